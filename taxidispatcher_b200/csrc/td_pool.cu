@@ -1,0 +1,770 @@
+// td_pool.cu -- K4: the 2..4-passenger pool finder.
+//
+// Replaces one pool_n process of the reference (pool_n.c:209-238):
+//   findPool        pool_n.c:153-177   ordered pickup tuples, cumulative-wait pruning
+//   drop_customers  pool_n.c:101-151   all K! drop-off orders, per-passenger detour test
+//   removeDuplicates pool_n.c:187-207  sort by cost (stable => ties by enumeration rank), greedy
+//                                      scan keeping plans that share no customer with a kept one
+//   shard rule      pool_n.c:226-229   leading customer in [step*t, min(n, step*t+step)), step = n/S + 1
+// and findpool.c:83-108 (merge of the shard outputs) in td_pool_merge.
+//
+// Formal statement: SURVEY.md section 8(a).  Notation: customer c has from F, to T, max wait W,
+// max loss L (percent); D = stand distance table; thr[c] = floor(D(F,T) * (1 + L/100.0)) in IEEE
+// fp64 -- the reference's int-vs-double compare `ride > D*(1+L/100.0)` (pool_n.c:115-116) is
+// exactly `ride > thr` for integer ride.
+//
+// Kernels
+//   pool_prep_cust     per customer {F, T, thr, W}
+//   pool_build_lists   per stand s: customers ordered by slack(s,c) = W[c] - D(s,F[c]) descending
+//                      (counting sort, 64 buckets) + cnt[s][w] = #{c : slack >= w}.  The wait rule
+//                      "cumulative pickup distance w + D(s,F[c]) <= W[c]" turns into "c is in the
+//                      first cnt[s][w] entries of list[s]": the next pickup level is a contiguous
+//                      prefix, no search, no test.
+//   pool_item_offsets  work items = (leader, position in list[F[leader]]) for K >= 3, leader for K = 2
+//   pool_enum<K>       one warp per item; outer pickup levels are warp-uniform loops, the LAST
+//                      pickup level is spread over the 32 lanes; each lane evaluates all K! drop-off
+//                      orders of its tuple in registers (fully unrolled, shared prefixes CSE'd).
+//                      Stand distances and customer records are staged in shared memory.
+//                      Every tuple materialises at most ONE record: its best feasible order under
+//                      (cost, permutation index).  The other feasible orders of the same tuple
+//                      cover the same customers with a larger key, so they can never survive the
+//                      greedy scan; they are counted (stats.feasible) but not stored.
+//   pool_select (coop) parallel greedy = rounds of "locally dominant" plans: a live plan whose key
+//                      (cost, rank) is the minimum over all live plans at each of its customers is
+//                      kept by the sequential scan regardless of anything else; keep all of them,
+//                      kill their customers, compact, repeat.  Equal to sort + greedy scan because
+//                      the key order is strict.  rank = (p0,p1,..,perm) lexicographic = the
+//                      enumeration order of pool_n.c, i.e. the tie order of a stable sort by cost.
+//   pool_emit          kept plans in key order -> 9-int records of pool_n.c:123-134
+//
+// Roofline: the enumeration is INT32-issue + shared-memory-lookup bound; compulsory HBM traffic is
+// ~0.4 B per plan.  SURVEY.md section 8(d) defines the logical bytes used for the HBM-fraction
+// figure: 80 B per evaluated plan (4 customers x the 5-int32 demand record) + 36 B per feasible plan.
+#include "td_common.cuh"
+#include <string.h>
+
+namespace cg = cooperative_groups;
+
+namespace td {
+
+constexpr int kTbl = 64;          // budget table entries per stand
+constexpr int kEnumThreads = 256;
+constexpr int kChunk = 128;       // records reserved per atomic
+constexpr int kSelThreads = 512;
+constexpr int kCustBits = 14;     // TD_POOL_MAX_CUSTOMERS = 16384
+constexpr int kPermBits = 5;
+
+struct PoolRec {                  // 16 bytes
+    unsigned long long rank;      // p0 | p1 | p2 | p3 | perm  (unused pickup slots are 0)
+    int32_t cost;                 // < 0: hole (unused slot of a reserved chunk)
+    int32_t pad;
+};
+
+struct PoolCtrl {
+    unsigned long long evaluated, feasible;
+    unsigned int n_records;       // slots reserved in the record list
+    unsigned int item_counter;
+    unsigned int overflow;
+    unsigned int n_items;
+    unsigned int n_kept;
+    unsigned int rounds;
+    unsigned int list_count[2];   // live records in the ping-pong lists of pool_select
+    int32_t max_wait;
+};
+
+__device__ __forceinline__ unsigned long long make_rank(int p0, int p1, int p2, int p3, int perm) {
+    return ((((((unsigned long long)p0 << kCustBits) | (unsigned)p1) << kCustBits | (unsigned)p2) << kCustBits |
+             (unsigned)p3) << kPermBits) | (unsigned)perm;
+}
+__device__ __forceinline__ void split_rank(unsigned long long r, int p[4], int &perm) {
+    perm = int(r & ((1u << kPermBits) - 1)); r >>= kPermBits;
+    const unsigned m = (1u << kCustBits) - 1;
+    p[3] = int(r & m); r >>= kCustBits;
+    p[2] = int(r & m); r >>= kCustBits;
+    p[1] = int(r & m); r >>= kCustBits;
+    p[0] = int(r & m);
+}
+
+// ---- prep ----------------------------------------------------------------------------------------
+__global__ void pool_prep_cust_kernel(const int32_t *__restrict__ demand, int n, const int32_t *__restrict__ dist,
+                                      int S, int4 *cust, PoolCtrl *ctrl) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    (void)ctrl;  // zeroed by the host-side memset
+    if (c >= n) return;
+    const int f = demand[c * 5 + 1], t = demand[c * 5 + 2], w = demand[c * 5 + 3], l = demand[c * 5 + 4];
+    const int d = dist[size_t(f) * S + t];
+    // pool_n.c:115-116: ride > d * (1 + l/100.0), evaluated in fp64 with round-to-nearest, no contraction
+    const double lim = __dmul_rn(double(d), __dadd_rn(1.0, __ddiv_rn(double(l), 100.0)));
+    double fl = floor(lim);
+    int thr;
+    if (fl >= 2147483647.0) thr = INT_MAX;
+    else if (fl < -2147483647.0) thr = INT_MIN;
+    else thr = int(fl);
+    cust[c] = make_int4(f, t, thr, w);
+}
+
+// one CTA per stand: counting sort of the customers reachable from this stand by slack, descending
+__global__ void __launch_bounds__(256)
+pool_build_lists_kernel(const int4 *__restrict__ cust, int n, const int32_t *__restrict__ dist, int S,
+                        int32_t *list, int32_t *slack_out, int32_t *cnt) {
+    __shared__ int hist[kTbl];
+    __shared__ int offs[kTbl];
+    const int s = blockIdx.x;
+    for (int b = threadIdx.x; b < kTbl; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const int4 r = cust[c];
+        const int sl = r.w - dist[size_t(s) * S + r.x];
+        if (sl >= 0) atomicAdd(&hist[sl < kTbl ? sl : kTbl - 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = kTbl - 1; b >= 0; --b) {  // descending slack: bucket b starts after all larger buckets
+            offs[b] = run;
+            run += hist[b];
+            cnt[size_t(s) * kTbl + b] = run;   // #{c : slack >= b}
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const int4 r = cust[c];
+        const int sl = r.w - dist[size_t(s) * S + r.x];
+        if (sl >= 0) {
+            const int pos = atomicAdd(&offs[sl < kTbl ? sl : kTbl - 1], 1);
+            list[size_t(s) * n + pos] = c;
+            slack_out[size_t(s) * n + pos] = sl;
+        }
+    }
+}
+
+// items per leader (exclusive prefix).  K >= 3: one item per (leader, first-level candidate).
+__global__ void pool_item_offsets_kernel(const int4 *__restrict__ cust, const int32_t *__restrict__ cnt, int start,
+                                         int stop, int pool_size, unsigned int *item_off, PoolCtrl *ctrl) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;  // <= n/n_shards+1 leaders: a serial scan is fine
+    unsigned run = 0;
+    for (int p0 = start; p0 < stop; ++p0) {
+        item_off[p0 - start] = run;
+        const int4 r = cust[p0];
+        if (r.w >= 0) run += pool_size >= 3 ? unsigned(cnt[size_t(r.x) * kTbl + 0]) : 1u;  // pool_n.c:172 at level 0
+    }
+    item_off[stop - start] = run;
+    ctrl->n_items = run;
+}
+
+// ---- enumeration ---------------------------------------------------------------------------------
+struct EnumArgs {
+    const int4 *cust; const int32_t *dist; const int32_t *list; const int32_t *slack; const int32_t *cnt;
+    const unsigned int *item_off; PoolRec *recs; PoolCtrl *ctrl;
+    int n, S, start, stop; unsigned int cap;
+};
+
+template <bool kDistSmem>
+struct DistView {
+    const int32_t *p; int S;
+    __device__ __forceinline__ int operator()(int a, int b) const {
+        return kDistSmem ? p[a * S + b] : __ldg(p + size_t(a) * S + b);
+    }
+};
+
+// candidates of the next pickup level from stand s with cumulative wait w: prefix length of list[s]
+__device__ __forceinline__ int cand_count(const int32_t *cnt, int s, int w) {
+    return cnt[s * kTbl + (w < 0 ? 0 : (w < kTbl ? w : kTbl - 1))];
+}
+
+struct WarpOut {  // per-warp slice of the record list
+    unsigned base, used;
+};
+
+__device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, bool has, unsigned long long rank, int cost,
+                                             int lane) {
+    const unsigned ball = __ballot_sync(0xffffffffu, has);
+    if (ball == 0) return;
+    const unsigned need = __popc(ball);
+    if (wo.used + need > kChunk) {
+        // abandon the rest of the current chunk (mark holes) and reserve a new one
+        if (wo.base != 0xffffffffu)
+            for (unsigned t = wo.used + lane; t < kChunk; t += 32) a.recs[wo.base + t].cost = -1;
+        unsigned nb = 0;
+        if (lane == 0) nb = atomicAdd(&a.ctrl->n_records, unsigned(kChunk));
+        nb = __shfl_sync(0xffffffffu, nb, 0);
+        if (nb + kChunk > a.cap) {
+            if (lane == 0) a.ctrl->overflow = 1;
+            wo.base = 0xffffffffu; wo.used = kChunk;  // drop records from now on (counts stay exact)
+            return;
+        }
+        wo.base = nb; wo.used = 0;
+    }
+    if (wo.base == 0xffffffffu) return;
+    if (has) {
+        const unsigned pos = wo.base + wo.used + __popc(ball & ((1u << lane) - 1));
+        PoolRec r; r.rank = rank; r.cost = cost; r.pad = 0;
+        *reinterpret_cast<int4 *>(a.recs + pos) = *reinterpret_cast<int4 *>(&r);
+    }
+    wo.used += need;
+}
+
+// K = 4: e[i] = D(F3,T_i); t[i][j] = D(T_i,T_j); slack[i] = thr_i - (pickup legs from i to the last pickup)
+__device__ __forceinline__ void eval4(const int e[4], const int t[4][4], const int sl[4], int pick_sum, int &nfeas,
+                                      int &best) {
+    nfeas = 0; best = INT_MAX;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d0 = e[i];
+        const bool ok0 = d0 <= sl[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j == i) continue;
+            const int d1 = d0 + t[i][j];
+            const bool ok1 = ok0 && d1 <= sl[j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k == i || k == j) continue;
+                const int l = 6 - i - j - k;
+                const int d2 = d1 + t[j][k];
+                const int d3 = d2 + t[k][l];
+                const bool ok = ok1 && d2 <= sl[k] && d3 <= sl[l];
+                // lexicographic permutation index (pool_n.c:137-150 order)
+                const int rj = j - (j > i);
+                const int rk = k - (k > i) - (k > j);
+                const int perm = i * 6 + rj * 2 + rk;
+                const int key = ((pick_sum + d3) << kPermBits) | perm;
+                nfeas += ok;
+                best = (ok && key < best) ? key : best;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void eval3(const int e[3], const int t[3][3], const int sl[3], int pick_sum, int &nfeas,
+                                      int &best) {
+    nfeas = 0; best = INT_MAX;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int d0 = e[i];
+        const bool ok0 = d0 <= sl[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j == i) continue;
+            const int k = 3 - i - j;
+            const int d1 = d0 + t[i][j];
+            const int d2 = d1 + t[j][k];
+            const bool ok = ok0 && d1 <= sl[j] && d2 <= sl[k];
+            const int perm = i * 2 + (j - (j > i));
+            const int key = ((pick_sum + d2) << kPermBits) | perm;
+            nfeas += ok;
+            best = (ok && key < best) ? key : best;
+        }
+    }
+}
+
+template <int K, bool kDistSmem, bool kCustSmem>
+__global__ void __launch_bounds__(kEnumThreads)
+pool_enum_kernel(EnumArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t *s_dist = reinterpret_cast<int32_t *>(smem_raw);
+    int4 *s_cust = reinterpret_cast<int4 *>(smem_raw + (kDistSmem ? ((size_t(a.S) * a.S * 4 + 15) & ~size_t(15)) : 0));
+    if (kDistSmem)
+        for (int i = threadIdx.x; i < a.S * a.S; i += kEnumThreads) s_dist[i] = a.dist[i];
+    if (kCustSmem)
+        for (int i = threadIdx.x; i < a.n; i += kEnumThreads) s_cust[i] = a.cust[i];
+    __syncthreads();
+    const DistView<kDistSmem> D{kDistSmem ? s_dist : a.dist, a.S};
+    const int4 *cust = kCustSmem ? s_cust : a.cust;
+    const int lane = threadIdx.x & 31;
+    const int n = a.n;
+    const unsigned n_items = a.ctrl->n_items;
+    const int n_lead = a.stop - a.start;
+    unsigned long long my_eval = 0, my_feas = 0;
+    WarpOut wo{0xffffffffu, unsigned(kChunk)};
+
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(&a.ctrl->item_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        // leader = last index with item_off[idx] <= item
+        int lo = 0, hi = n_lead;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
+        }
+        const int p0 = a.start + lo;
+        const int4 c0 = cust[p0];
+
+        if (K == 2) {
+            // lanes over p1
+            const int n1 = cand_count(a.cnt, c0.x, 0);
+            for (int t1 = lane; t1 < ((n1 + 31) & ~31); t1 += 32) {
+                bool valid = t1 < n1;
+                int p1 = 0;
+                if (valid) { p1 = a.list[size_t(c0.x) * n + t1]; valid = p1 != p0; }
+                int nfeas = 0, best = INT_MAX;
+                if (valid) {
+                    const int4 c1 = cust[p1];
+                    const int a01 = D(c0.x, c1.x);
+                    const int sl0 = c0.z - a01, sl1 = c1.z;
+                    const int e0 = D(c1.x, c0.y), e1 = D(c1.x, c1.y);
+                    const int t01 = D(c0.y, c1.y), t10 = D(c1.y, c0.y);
+                    // perm 0: drop 0 then 1; perm 1: drop 1 then 0
+                    const bool okA = e0 <= sl0 && e0 + t01 <= sl1;
+                    const bool okB = e1 <= sl1 && e1 + t10 <= sl0;
+                    const int kA = ((a01 + e0 + t01) << kPermBits) | 0, kB = ((a01 + e1 + t10) << kPermBits) | 1;
+                    nfeas = int(okA) + int(okB);
+                    if (okA) best = kA;
+                    if (okB && kB < best) best = kB;
+                    my_eval += 2;
+                    my_feas += nfeas;
+                }
+                emit_records(a, wo, nfeas > 0, make_rank(p0, p1, 0, 0, best & 31), best >> kPermBits, lane);
+            }
+            continue;
+        }
+
+        const int t1 = int(item - a.item_off[lo]);
+        const int p1 = a.list[size_t(c0.x) * n + t1];
+        if (p1 == p0) continue;
+        const int4 c1 = cust[p1];
+        const int a01 = D(c0.x, c1.x);  // <= W[p1] by construction of the prefix
+        const int t01 = D(c0.y, c1.y), t10 = D(c1.y, c0.y);
+
+        if (K == 3) {
+            const int n2 = cand_count(a.cnt, c1.x, a01);
+            for (int t2 = lane; t2 < ((n2 + 31) & ~31); t2 += 32) {
+                bool valid = t2 < n2;
+                int p2 = 0;
+                if (valid) {
+                    p2 = a.list[size_t(c1.x) * n + t2];
+                    valid = p2 != p0 && p2 != p1 && (a01 < kTbl || a.slack[size_t(c1.x) * n + t2] >= a01);
+                }
+                int nfeas = 0, best = INT_MAX;
+                if (valid) {
+                    const int4 c2 = cust[p2];
+                    const int a12 = D(c1.x, c2.x);
+                    int e[3], t[3][3], sl[3];
+                    e[0] = D(c2.x, c0.y); e[1] = D(c2.x, c1.y); e[2] = D(c2.x, c2.y);
+                    t[0][0] = t[1][1] = t[2][2] = 0;
+                    t[0][1] = t01; t[1][0] = t10;
+                    t[0][2] = D(c0.y, c2.y); t[2][0] = D(c2.y, c0.y);
+                    t[1][2] = D(c1.y, c2.y); t[2][1] = D(c2.y, c1.y);
+                    sl[2] = c2.z; sl[1] = c1.z - a12; sl[0] = c0.z - a01 - a12;
+                    eval3(e, t, sl, a01 + a12, nfeas, best);
+                    my_eval += 6;
+                    my_feas += nfeas;
+                }
+                emit_records(a, wo, nfeas > 0, make_rank(p0, p1, p2, 0, best & 31), best >> kPermBits, lane);
+            }
+            continue;
+        }
+
+        // K == 4: warp-uniform loop over p2, lanes over p3
+        const int n2 = cand_count(a.cnt, c1.x, a01);
+        for (int t2 = 0; t2 < n2; ++t2) {
+            const int p2 = a.list[size_t(c1.x) * n + t2];
+            if (p2 == p0 || p2 == p1) continue;
+            if (a01 >= kTbl && a.slack[size_t(c1.x) * n + t2] < a01) continue;
+            const int4 c2 = cust[p2];
+            const int a12 = D(c1.x, c2.x);
+            const int w2 = a01 + a12;
+            const int t02 = D(c0.y, c2.y), t20 = D(c2.y, c0.y), t12 = D(c1.y, c2.y), t21 = D(c2.y, c1.y);
+            const int n3 = cand_count(a.cnt, c2.x, w2);
+            for (int t3 = lane; t3 < ((n3 + 31) & ~31); t3 += 32) {
+                bool valid = t3 < n3;
+                int p3 = 0;
+                if (valid) {
+                    p3 = a.list[size_t(c2.x) * n + t3];
+                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2 < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2);
+                }
+                int nfeas = 0, best = INT_MAX;
+                if (valid) {
+                    const int4 c3 = cust[p3];
+                    const int a23 = D(c2.x, c3.x);
+                    int e[4], t[4][4], sl[4];
+                    e[0] = D(c3.x, c0.y); e[1] = D(c3.x, c1.y); e[2] = D(c3.x, c2.y); e[3] = D(c3.x, c3.y);
+                    t[0][0] = t[1][1] = t[2][2] = t[3][3] = 0;
+                    t[0][1] = t01; t[1][0] = t10; t[0][2] = t02; t[2][0] = t20; t[1][2] = t12; t[2][1] = t21;
+                    t[0][3] = D(c0.y, c3.y); t[3][0] = D(c3.y, c0.y);
+                    t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
+                    t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
+                    sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - w2 - a23;
+                    eval4(e, t, sl, w2 + a23, nfeas, best);
+                    my_eval += 24;
+                    my_feas += nfeas;
+                }
+                emit_records(a, wo, nfeas > 0, make_rank(p0, p1, p2, p3, best & 31), best >> kPermBits, lane);
+            }
+        }
+    }
+    // close the last chunk, publish the counters
+    if (wo.base != 0xffffffffu)
+        for (unsigned t = wo.used + lane; t < kChunk; t += 32) a.recs[wo.base + t].cost = -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
+        my_feas += __shfl_xor_sync(0xffffffffu, my_feas, o);
+    }
+    if (lane == 0) {
+        if (my_eval) atomicAdd(&a.ctrl->evaluated, my_eval);
+        if (my_feas) atomicAdd(&a.ctrl->feasible, my_feas);
+    }
+}
+
+// ---- selection -----------------------------------------------------------------------------------
+struct SelArgs {
+    PoolRec *list[2]; PoolCtrl *ctrl;
+    unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolRec *kept;
+    int n, K;
+};
+
+__device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
+    return ((unsigned long long)(unsigned)r.cost << 32) | (r.rank >> 32);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+pool_select_kernel(SelArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31;
+    const int K = a.K;
+    for (unsigned c = tid; c < unsigned(a.n); c += nthreads) {
+        a.alive[c] = 1;
+        a.best_hi[0][c] = a.best_hi[1][c] = ~0ull;
+        a.best_lo[0][c] = a.best_lo[1][c] = ~0u;
+    }
+    if (tid == 0) { a.ctrl->list_count[0] = a.ctrl->overflow ? 0u : a.ctrl->n_records; a.ctrl->list_count[1] = 0; }
+    grid.sync();
+    unsigned cur = 0;
+    for (unsigned round = 0;; ++round) {
+        const unsigned b = round & 1;
+        const unsigned cnt = a.ctrl->list_count[cur];
+        if (cnt == 0) { if (tid == 0) a.ctrl->rounds = round; break; }
+        const PoolRec *src = a.list[cur];
+        PoolRec *dst = a.list[cur ^ 1];
+        // pass A: drop holes / dead plans, compact the live ones, first-level key minimum per customer
+        for (unsigned base = blockIdx.x * blockDim.x; base < cnt; base += nthreads) {
+            const unsigned i = base + threadIdx.x;
+            bool live = false;
+            PoolRec r;
+            int p[4], perm;
+            if (i < cnt) {
+                r = src[i];
+                if (r.cost >= 0) {
+                    split_rank(r.rank, p, perm);
+                    live = true;
+                    for (int q = 0; q < K; ++q) live = live && a.alive[p[q]];
+                }
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, live);
+            unsigned wbase = 0;
+            if (lane == 0 && ball) wbase = atomicAdd(&a.ctrl->list_count[cur ^ 1], __popc(ball));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (live) {
+                dst[wbase + __popc(ball & ((1u << lane) - 1))] = r;
+                const unsigned long long hi = rec_hi(r);
+                for (int q = 0; q < K; ++q)
+                    if (hi < a.best_hi[b][p[q]]) atomicMin(&a.best_hi[b][p[q]], hi);
+            }
+        }
+        grid.sync();
+        const unsigned live_cnt = a.ctrl->list_count[cur ^ 1];
+        // pass B: second-level minimum among the plans that tie on the first level
+        for (unsigned i = tid; i < live_cnt; i += nthreads) {
+            const PoolRec r = dst[i];
+            int p[4], perm;
+            split_rank(r.rank, p, perm);
+            const unsigned long long hi = rec_hi(r);
+            const unsigned lo = unsigned(r.rank);
+            for (int q = 0; q < K; ++q)
+                if (a.best_hi[b][p[q]] == hi && lo < a.best_lo[b][p[q]]) atomicMin(&a.best_lo[b][p[q]], lo);
+        }
+        if (tid == 0) a.ctrl->list_count[cur] = 0;  // becomes the destination of the next round
+        grid.sync();
+        // pass C: keep the plans that hold the minimum at every one of their customers
+        for (unsigned i = tid; i < live_cnt; i += nthreads) {
+            const PoolRec r = dst[i];
+            int p[4], perm;
+            split_rank(r.rank, p, perm);
+            const unsigned long long hi = rec_hi(r);
+            const unsigned lo = unsigned(r.rank);
+            bool dom = true;
+            for (int q = 0; q < K; ++q) dom = dom && a.best_hi[b][p[q]] == hi && a.best_lo[b][p[q]] == lo;
+            if (dom) {
+                const unsigned slot = atomicAdd(&a.ctrl->n_kept, 1u);
+                a.kept[slot] = r;
+                for (int q = 0; q < K; ++q) a.alive[p[q]] = 0;
+            }
+        }
+        // reset the other parity's minima for the next round (nobody reads them in this round)
+        for (unsigned c = tid; c < unsigned(a.n); c += nthreads) { a.best_hi[b ^ 1][c] = ~0ull; a.best_lo[b ^ 1][c] = ~0u; }
+        grid.sync();
+        cur ^= 1;
+    }
+}
+
+// kept plans -> ascending (cost, rank) -> pool_n.c:123-134 records
+__global__ void __launch_bounds__(1024)
+pool_emit_kernel(const PoolRec *__restrict__ kept, const PoolCtrl *ctrl, int K, int32_t *plans_out, int32_t cap,
+                 int32_t *n_plans_out) {
+    const int m = int(ctrl->n_kept);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const PoolRec me = kept[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) {
+            const PoolRec o = kept[j];
+            rank += (o.cost < me.cost) || (o.cost == me.cost && o.rank < me.rank);
+        }
+        if (rank < cap) {
+            int p[4], perm;
+            split_rank(me.rank, p, perm);
+            // decode the lexicographic permutation index into the drop-off order
+            int q[4] = {0, 0, 0, 0};
+            bool used[4] = {false, false, false, false};
+            int fact = 1;
+            for (int f = 2; f < K; ++f) fact *= f;  // (K-1)!
+            int rem = perm;
+            for (int lvl = 0; lvl < K; ++lvl) {
+                int idx = rem / fact; rem -= idx * fact;
+                if (K - 1 - lvl > 0) fact /= (K - 1 - lvl);
+                int c = 0;
+                for (int cand = 0; cand < K; ++cand) {
+                    if (used[cand]) continue;
+                    if (c == idx) { q[lvl] = cand; used[cand] = true; break; }
+                    ++c;
+                }
+            }
+            int32_t *row = plans_out + size_t(rank) * TD_POOL_REC_W;
+            for (int t = 0; t < TD_POOL_REC_W; ++t) row[t] = 0;
+            for (int t = 0; t < K; ++t) { row[t] = p[t]; row[t + K] = p[q[t]]; }
+            row[8] = me.cost;
+        }
+    }
+    if (threadIdx.x == 0) *n_plans_out = ctrl->overflow ? -1 : m;  // -1: record list overflowed, result invalid
+}
+
+// ---- merge (findpool.c:83-108) ---------------------------------------------------------------
+// total <= n_shards * n / K rows; runs in one CTA: stable order by column 8 (or concatenation
+// order for K < 4, see header), then the same dominance rounds on the tiny list.
+__global__ void __launch_bounds__(1024)
+pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, int32_t *order_key /* total */,
+                  int32_t *owner /* n */, uint8_t *state /* total: 0 live, 1 kept, 2 dead */, int32_t *plans_out,
+                  int32_t *n_plans_out) {
+    __shared__ int s_live;
+    const int tid = threadIdx.x;
+    // position of every row in the scan order: (cost, concatenation index) for K == 4, index otherwise
+    for (int i = tid; i < total; i += blockDim.x) {
+        int pos = i;
+        if (K == TD_POOL_MAX_IN_POOL) {
+            const int ci = plans[size_t(i) * TD_POOL_REC_W + 8];
+            pos = 0;
+            for (int j = 0; j < total; ++j) {
+                const int cj = plans[size_t(j) * TD_POOL_REC_W + 8];
+                pos += (cj < ci) || (cj == ci && j < i);
+            }
+        }
+        order_key[i] = pos;
+        state[i] = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        for (int c = tid; c < n; c += blockDim.x) owner[c] = INT_MAX;
+        if (tid == 0) s_live = 0;
+        __syncthreads();
+        for (int i = tid; i < total; i += blockDim.x)
+            if (state[i] == 0) {
+                s_live = 1;
+                for (int q = 0; q < K; ++q) atomicMin(&owner[plans[size_t(i) * TD_POOL_REC_W + q]], order_key[i]);
+            }
+        __syncthreads();
+        if (!s_live) break;
+        for (int i = tid; i < total; i += blockDim.x)
+            if (state[i] == 0) {
+                bool dom = true;
+                for (int q = 0; q < K; ++q) dom = dom && owner[plans[size_t(i) * TD_POOL_REC_W + q]] == order_key[i];
+                if (dom) state[i] = 1;
+            }
+        __syncthreads();
+        // mark customers of kept plans, then kill the live plans touching them
+        for (int c = tid; c < n; c += blockDim.x) owner[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < total; i += blockDim.x)
+            if (state[i] == 1)
+                for (int q = 0; q < K; ++q) owner[plans[size_t(i) * TD_POOL_REC_W + q]] = 1;
+        __syncthreads();
+        for (int i = tid; i < total; i += blockDim.x)
+            if (state[i] == 0) {
+                bool hit = false;
+                for (int q = 0; q < K; ++q) hit = hit || owner[plans[size_t(i) * TD_POOL_REC_W + q]] == 1;
+                if (hit) state[i] = 2;
+            }
+        __syncthreads();
+    }
+    // output the kept rows in scan order
+    for (int i = tid; i < total; i += blockDim.x)
+        if (state[i] == 1) {
+            int pos = 0;
+            for (int j = 0; j < total; ++j) pos += (state[j] == 1 && order_key[j] < order_key[i]);
+            for (int t = 0; t < TD_POOL_REC_W; ++t) plans_out[size_t(pos) * TD_POOL_REC_W + t] = plans[size_t(i) * TD_POOL_REC_W + t];
+        }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int i = 0; i < total; ++i) m += state[i] == 1;
+        *n_plans_out = m;
+    }
+}
+
+struct PoolWorkspace {
+    int4 *cust; int32_t *list, *slack, *cnt; unsigned int *item_off; PoolRec *recs[2]; PoolRec *kept;
+    unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolCtrl *ctrl; size_t bytes;
+};
+
+static PoolWorkspace carve_pool(void *ws, int n, int S, int64_t max_feasible) {
+    Carver c(ws);
+    PoolWorkspace w;
+    const size_t nn = n > 0 ? n : 1;
+    w.ctrl = c.take<PoolCtrl>(1);
+    w.cust = c.take<int4>(nn);
+    w.list = c.take<int32_t>(size_t(S) * nn);
+    w.slack = c.take<int32_t>(size_t(S) * nn);
+    w.cnt = c.take<int32_t>(size_t(S) * kTbl);
+    w.item_off = c.take<unsigned int>(nn + 2);
+    w.recs[0] = c.take<PoolRec>(size_t(max_feasible));
+    w.recs[1] = c.take<PoolRec>(size_t(max_feasible));
+    w.kept = c.take<PoolRec>(nn);
+    w.best_hi[0] = c.take<unsigned long long>(nn);
+    w.best_hi[1] = c.take<unsigned long long>(nn);
+    w.best_lo[0] = c.take<unsigned int>(nn);
+    w.best_lo[1] = c.take<unsigned int>(nn);
+    w.alive = c.take<uint8_t>(nn);
+    w.bytes = c.used();
+    return w;
+}
+
+template <int K>
+static int launch_enum(const EnumArgs &a, int grid, cudaStream_t st) {
+    const size_t dist_b = (size_t(a.S) * a.S * 4 + 15) & ~size_t(15);
+    const size_t cust_b = size_t(a.n) * 16;
+    const bool ds = dist_b <= 64 * 1024;
+    const bool cs = cust_b <= 96 * 1024;
+    const size_t smem = (ds ? dist_b : 0) + (cs ? cust_b : 0);
+#define TD_ENUM_CASE(DS, CS)                                                                                             \
+    do {                                                                                                                 \
+        TD_CUDA_TRY(cudaFuncSetAttribute(pool_enum_kernel<K, DS, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         int(200 * 1024)));                                                              \
+        pool_enum_kernel<K, DS, CS><<<grid, kEnumThreads, smem, st>>>(a);                                                \
+    } while (0)
+    if (ds && cs) TD_ENUM_CASE(true, true);
+    else if (ds) TD_ENUM_CASE(true, false);
+    else if (cs) TD_ENUM_CASE(false, true);
+    else TD_ENUM_CASE(false, false);
+#undef TD_ENUM_CASE
+    TD_LAUNCH_CHECK();
+    return TD_OK;
+}
+
+}  // namespace td
+
+extern "C" size_t td_pool_workspace_bytes(int n, int n_stands, int pool_size, int64_t max_feasible) {
+    (void)pool_size;
+    if (n < 0 || n_stands < 0 || max_feasible < 0) return 0;
+    // chunked reservation can strand up to one chunk per resident warp
+    const int64_t slack = int64_t(td::kChunk) * 148 * 64;
+    return td::carve_pool(nullptr, n, n_stands, max_feasible + slack).bytes;
+}
+
+extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size, int shard,
+                            int n_shards, int32_t *plans_out, int32_t cap, int32_t *n_plans_out, td_pool_stats *stats,
+                            void *workspace, size_t workspace_bytes, int64_t max_feasible, void *stream) {
+    using namespace td;
+    if (pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || n < 0 || n > TD_POOL_MAX_CUSTOMERS || n_stands <= 0 ||
+        n_shards < 1 || shard < 0 || shard >= n_shards || cap < 0 || !n_plans_out || max_feasible < 0)
+        return TD_ERR_INVALID;
+    if (n_stands > 32767) return TD_ERR_INVALID;
+    if (!have_device()) return TD_ERR_NO_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (stats) memset(stats, 0, sizeof *stats);
+    const int step = n / n_shards + 1;                       // pool_n.c:226
+    const int start = step * shard;                          // pool_n.c:227
+    const int stop = start + step > n ? n : start + step;    // pool_n.c:228
+    if (n == 0 || start >= n) {
+        TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st));
+        if (stats) TD_CUDA_TRY(cudaStreamSynchronize(st));
+        return TD_OK;
+    }
+    if (!demand || !dist || !workspace || (cap > 0 && !plans_out)) return TD_ERR_INVALID;
+    if (workspace_bytes < td_pool_workspace_bytes(n, n_stands, pool_size, max_feasible)) return TD_ERR_WORKSPACE;
+    const int64_t rec_cap64 = max_feasible + int64_t(kChunk) * 148 * 64;
+    if (rec_cap64 > 0xfffffff0ll) return TD_ERR_INVALID;
+    PoolWorkspace w = carve_pool(workspace, n, n_stands, rec_cap64);
+
+    TD_CUDA_TRY(cudaMemsetAsync(w.ctrl, 0, sizeof(PoolCtrl), st));
+    pool_prep_cust_kernel<<<(n + 255) / 256, 256, 0, st>>>(demand, n, dist, n_stands, w.cust, w.ctrl);
+    TD_LAUNCH_CHECK();
+    pool_build_lists_kernel<<<n_stands, 256, 0, st>>>(w.cust, n, dist, n_stands, w.list, w.slack, w.cnt);
+    TD_LAUNCH_CHECK();
+    pool_item_offsets_kernel<<<1, 32, 0, st>>>(w.cust, w.cnt, start, stop, pool_size, w.item_off, w.ctrl);
+    TD_LAUNCH_CHECK();
+
+    EnumArgs ea;
+    ea.cust = w.cust; ea.dist = dist; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
+    ea.recs = w.recs[0]; ea.ctrl = w.ctrl; ea.n = n; ea.S = n_stands; ea.start = start; ea.stop = stop;
+    ea.cap = unsigned(rec_cap64);
+    const int sms = device_sm_count();
+    const int grid = sms * 4;
+    int rc = pool_size == 4 ? launch_enum<4>(ea, grid, st) : pool_size == 3 ? launch_enum<3>(ea, grid, st) : launch_enum<2>(ea, grid, st);
+    if (rc != TD_OK) return rc;
+
+    SelArgs sa;
+    sa.list[0] = w.recs[0]; sa.list[1] = w.recs[1]; sa.ctrl = w.ctrl;
+    sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
+    sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = pool_size;
+    int per_sm = 0;
+    TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_select_kernel, kSelThreads, 0));
+    if (per_sm < 1) return TD_ERR_CUDA;
+    per_sm = per_sm > 2 ? 2 : per_sm;
+    void *sargs[] = {(void *)&sa};
+    TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)pool_select_kernel, dim3(sms * per_sm), dim3(kSelThreads), sargs, 0, st));
+    count_launch();
+    pool_emit_kernel<<<1, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, plans_out, cap, n_plans_out);
+    TD_LAUNCH_CHECK();
+
+    if (stats) {
+        PoolCtrl h;
+        TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
+        TD_CUDA_TRY(cudaStreamSynchronize(st));
+        stats->evaluated = int64_t(h.evaluated);
+        stats->feasible = int64_t(h.feasible);
+        stats->kept = h.n_kept;
+        stats->rounds = int32_t(h.rounds);
+        stats->passes = 1;
+        if (h.overflow) return TD_ERR_CAPACITY;
+        if (int64_t(h.n_kept) > cap) return TD_ERR_CAPACITY;
+    }
+    return TD_OK;
+}
+
+extern "C" size_t td_pool_merge_workspace_bytes(int total_plans, int n) {
+    td::Carver c(nullptr);
+    c.take<int32_t>(total_plans > 0 ? total_plans : 1);
+    c.take<int32_t>(n > 0 ? n : 1);
+    c.take<uint8_t>(total_plans > 0 ? total_plans : 1);
+    return c.used();
+}
+
+extern "C" int td_pool_merge(const int32_t *shard_plans, int total_plans, int n, int pool_size, int32_t *plans_out,
+                             int32_t *n_plans_out, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace td;
+    if (total_plans < 0 || n < 0 || pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || !n_plans_out) return TD_ERR_INVALID;
+    if (!have_device()) return TD_ERR_NO_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (total_plans == 0) { TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st)); return TD_OK; }
+    if (!shard_plans || !plans_out || !workspace) return TD_ERR_INVALID;
+    if (workspace_bytes < td_pool_merge_workspace_bytes(total_plans, n)) return TD_ERR_WORKSPACE;
+    Carver c(workspace);
+    int32_t *order_key = c.take<int32_t>(total_plans);
+    int32_t *owner = c.take<int32_t>(n > 0 ? n : 1);
+    uint8_t *state = c.take<uint8_t>(total_plans);
+    pool_merge_kernel<<<1, 1024, 0, st>>>(shard_plans, total_plans, n, pool_size, order_key, owner, state, plans_out, n_plans_out);
+    TD_LAUNCH_CHECK();
+    return TD_OK;
+}

@@ -1,0 +1,316 @@
+"""The reference's Python-level dispatch surface on top of libtaxidispatch.so (B200, sm_100a).
+
+Host functions mirror the reference's names, argument order and return layouts
+(SURVEY.md section 8(b)):
+
+  calculate_cost(distances, demand, cabs)          split.py:123-136, simulate.py:17-33
+  solve(n, cost) -> x                              solver.py:11-27   (x[n*cab+cust] in {0,1})
+  solve_dispatch(distances, demand, cabs)          split.py:139-155  -> (n, x, cost)
+  LCM(n, c, ...)                                   heuristic.py:24-33, split.py:161-175,
+                                                   greedy_opt.py:61-82, simulate.py:76-97
+  LCM_java(cost)                                   Simulator.java:523-549
+  find_pool(...) / find_pool_all(...) / pool_merge(...)   pool_n.c / findpool.c
+
+PyTorch is used only for device buffers, pinned staging and streams.  All arithmetic runs in the
+hand-written CUDA kernels behind the C ABI (include/taxidispatch.h).  There is no CPU fallback:
+without the built library or without a CUDA device these functions raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BIG_COST, INT32_MAX, POOL_REC_W, AssignStats, LcmParams, PoolStats, TaxiDispatchError, check
+
+__all__ = ["BIG_COST", "Engine", "calculate_cost", "solve", "solve_dispatch", "solve_full", "LCM", "LCM_heuristic",
+           "LCM_split", "LCM_greedy_opt", "LCM_simulate", "LCM_java", "find_pool", "find_pool_all", "pool_merge",
+           "TaxiDispatchError"]
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise TaxiDispatchError(_lib.TD_ERR_NO_DEVICE, "taxidispatcher_b200",
+                                "torch sees no CUDA device; this engine has no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _h2d_i32(a, pinned: bool = True) -> torch.Tensor:
+    """Host array-like -> int32 CUDA tensor through pinned staging (asynchronous copy)."""
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+    t = torch.from_numpy(arr)
+    if pinned and arr.size:
+        t = t.pin_memory()
+    return t.to("cuda", non_blocking=True)
+
+
+class Engine:
+    """Device-pointer front end: torch CUDA tensors in, torch CUDA tensors out, workspaces cached
+    per (operation, size) so that steady-state calls allocate nothing."""
+
+    def __init__(self, device: Optional[int] = None):
+        _require_cuda()
+        self.lib = _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._ws = {}
+
+    # -- scratch --------------------------------------------------------------------------------
+    def _workspace(self, key, nbytes: int) -> torch.Tensor:
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    # -- K1 ---------------------------------------------------------------------------------------
+    def cost_matrix(self, dist: torch.Tensor, cab_to: torch.Tensor, cust_from: torch.Tensor, fill: int = BIG_COST,
+                    cutoff: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n_cabs, n_cust = int(cab_to.numel()), int(cust_from.numel())
+        n = max(n_cabs, n_cust)
+        n_stands = int(dist.shape[0]) if dist.numel() else 0
+        if out is None:
+            out = torch.empty((n, n), dtype=torch.int32, device=self.device)
+        rc = self.lib.td_cost_matrix(_ptr(dist), n_stands, _ptr(cab_to), n_cabs, _ptr(cust_from), n_cust, int(fill),
+                                     -1 if cutoff is None else int(cutoff), _ptr(out), _stream())
+        check(rc, "td_cost_matrix")
+        return out
+
+    # -- K3 ---------------------------------------------------------------------------------------
+    def lcm(self, cost: torch.Tensor, mask_value: int, stop_above: int = INT32_MAX, stop_at_value: int = INT32_MAX,
+            sum_below: int = INT32_MAX, residual_size: int = 0, max_iters: int = -1):
+        """Returns device tensors (rows[n], cols[n], scal) where scal = int64[2] {total, n_pairs | last_min << 32}.
+        Use lcm_host_view() to decode after a synchronisation."""
+        n = int(cost.shape[0])
+        rows = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        cols = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        scal = torch.zeros(4, dtype=torch.int32, device=self.device)  # [total lo, total hi, n_pairs, last_min]
+        prm = LcmParams(int(mask_value), int(stop_above), int(stop_at_value), int(sum_below), int(residual_size),
+                        int(max_iters))
+        nbytes = self.lib.td_lcm_workspace_bytes(n)
+        ws = self._workspace(("lcm", n), nbytes)
+        base = scal.data_ptr()
+        rc = self.lib.td_lcm(_ptr(cost), n, ctypes.byref(prm), _ptr(rows), _ptr(cols), ctypes.c_void_p(base + 8),
+                             ctypes.c_void_p(base), ctypes.c_void_p(base + 12), _ptr(ws), ws.numel(), _stream())
+        check(rc, "td_lcm")
+        return rows, cols, scal
+
+    @staticmethod
+    def lcm_host_view(rows, cols, scal):
+        s = scal.cpu().numpy()
+        total = int(np.frombuffer(s[:2].tobytes(), dtype=np.int64)[0])
+        k = int(s[2])
+        return {"total": total, "n_pairs": k, "last_min": int(s[3]), "rows": rows[:k].cpu().numpy(),
+                "cols": cols[:k].cpu().numpy()}
+
+    # -- K2 ---------------------------------------------------------------------------------------
+    def assign(self, cost: torch.Tensor, want_x: bool = False, want_stats: bool = False):
+        n = int(cost.shape[0])
+        col = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        obj = torch.zeros(1, dtype=torch.int64, device=self.device)
+        x = torch.empty(n * n, dtype=torch.uint8, device=self.device) if want_x else None
+        nbytes = self.lib.td_assign_workspace_bytes(n)
+        ws = self._workspace(("assign", n), nbytes)
+        st = AssignStats() if want_stats else None
+        rc = self.lib.td_assign_exact(_ptr(cost), n, _ptr(col), _ptr(obj), _ptr(x),
+                                      ctypes.byref(st) if st is not None else None, _ptr(ws), ws.numel(), _stream())
+        check(rc, "td_assign_exact")
+        return col[:n], obj, x, st
+
+    # -- K4 ---------------------------------------------------------------------------------------
+    def pool_find(self, demand: torch.Tensor, dist: torch.Tensor, pool_size: int, shard: int = 0, n_shards: int = 8,
+                  max_feasible: Optional[int] = None, out: Optional[torch.Tensor] = None, want_stats: bool = True):
+        n = int(demand.shape[0])
+        n_stands = int(dist.shape[0])
+        cap = n // 2 + 1
+        if out is None:
+            out = torch.empty((cap, POOL_REC_W), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        mf = int(max_feasible) if max_feasible is not None else self._ws.get(("pool_mf", n, pool_size), 1 << 21)
+        for _ in range(8):
+            nbytes = self.lib.td_pool_workspace_bytes(n, n_stands, pool_size, mf)
+            ws = self._workspace(("pool", n, n_stands, pool_size), nbytes)
+            st = PoolStats()
+            rc = self.lib.td_pool_find(_ptr(demand), n, _ptr(dist), n_stands, pool_size, shard, n_shards, _ptr(out),
+                                       int(out.shape[0]), _ptr(cnt), ctypes.byref(st) if want_stats else None,
+                                       _ptr(ws), ws.numel(), mf, _stream())
+            if rc == _lib.TD_ERR_CAPACITY and want_stats and st.feasible > mf:
+                mf = int(st.feasible) + 1024          # grow the materialised list and retry
+                self._ws[("pool_mf", n, pool_size)] = mf
+                continue
+            check(rc, "td_pool_find")
+            return out, cnt, (st if want_stats else None)
+        raise TaxiDispatchError(_lib.TD_ERR_CAPACITY, "td_pool_find")
+
+    def pool_merge(self, shard_plans: torch.Tensor, total: int, n: int, pool_size: int):
+        out = torch.empty((max(total, 1), POOL_REC_W), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nbytes = self.lib.td_pool_merge_workspace_bytes(total, n)
+        ws = self._workspace(("merge", total, n), nbytes)
+        rc = self.lib.td_pool_merge(_ptr(shard_plans), total, n, pool_size, _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(),
+                                    _stream())
+        check(rc, "td_pool_merge")
+        return out, cnt
+
+
+_engine: Optional[Engine] = None
+
+
+def engine() -> Engine:
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+    return _engine
+
+
+# ================================================================================================
+# reference-shaped host API
+# ================================================================================================
+def calculate_cost(distances, demand: Sequence, cabs: Sequence, fill: int = BIG_COST, cutoff: Optional[int] = None,
+                   as_list: bool = False):
+    """split.py:123-136: (n, cost) with cost[c_idx][d_idx] = distances[cab.to][customer.from],
+    square-padded with `fill` (big_cost).  cutoff=DROP_TIME gives simulate.py:27 / Simulator.java:509.
+    demand / cabs are lists of (id, from, to); indexing is positional.  n == 0 -> (0, 0)
+    (simulate.py:21).  cost is an int32 ndarray (list of rows with as_list=True)."""
+    n_cabs, n_cust = len(cabs), len(demand)
+    n = max(n_cabs, n_cust)
+    if n == 0:
+        return 0, 0
+    eng = engine()
+    dist = _h2d_i32(distances)
+    cab_to = _h2d_i32([c[2] for c in cabs]) if n_cabs else torch.empty(0, dtype=torch.int32, device=eng.device)
+    cust_from = _h2d_i32([d[1] for d in demand]) if n_cust else torch.empty(0, dtype=torch.int32, device=eng.device)
+    if n_cabs and n_cust:
+        s = int(dist.shape[0])
+        if int(cab_to.max()) >= s or int(cab_to.min()) < 0 or int(cust_from.max()) >= s or int(cust_from.min()) < 0:
+            raise IndexError("stand index out of range of the distance table")  # the reference raises IndexError too
+    cost = eng.cost_matrix(dist, cab_to, cust_from, fill, cutoff).cpu().numpy()
+    return n, (cost.tolist() if as_list else cost)
+
+
+def solve_full(n: int, cost):
+    """Exact optimum; returns (x, col_of_row, objective, stats).  x is the reference vector."""
+    if n == 0:
+        return np.zeros(0, np.uint8), np.zeros(0, np.int32), 0, None
+    eng = engine()
+    c = _h2d_i32(np.asarray(cost).reshape(n, n))
+    col, obj, x, st = eng.assign(c, want_x=True, want_stats=True)
+    return x.cpu().numpy(), col.cpu().numpy(), int(obj.item()), st
+
+
+def solve(n: int, cost):
+    """solver.py:11-27: `x` with x[n*cab + cust] == 1 for the chosen cells.  n == 0 -> (0, [])
+    exactly like solver.py:12."""
+    if n == 0:
+        return 0, []
+    return solve_full(n, cost)[0]
+
+
+def solve_dispatch(distances, demand, cabs, fill: int = BIG_COST, cutoff: Optional[int] = None):
+    """split.py:139-155 / simulate.py:36-53: (n, x, cost).  n == 0 -> (0, [], 0) (simulate.py:38)."""
+    n, cost = calculate_cost(distances, demand, cabs, fill, cutoff)
+    if n == 0:
+        return 0, [], 0
+    return n, solve(n, cost), cost
+
+
+def LCM(n: int, c, mask_value: int = BIG_COST, stop_above: int = INT32_MAX, stop_at_value: int = INT32_MAX,
+        sum_below: int = INT32_MAX, residual_size: int = 0, max_iters: int = -1):
+    """Generic LCM; c is an n x n matrix (or flat n*n) whose row-major flattening is cost[cab][cust].
+    Returns dict(total, n_pairs, rows, cols, last_min)."""
+    if n == 0:
+        return {"total": 0, "n_pairs": 0, "rows": np.zeros(0, np.int32), "cols": np.zeros(0, np.int32),
+                "last_min": INT32_MAX}
+    eng = engine()
+    cost = _h2d_i32(np.asarray(c).reshape(n, n))
+    return Engine.lcm_host_view(*eng.lcm(cost, mask_value, stop_above, stop_at_value, sum_below, residual_size, max_iters))
+
+
+def LCM_heuristic(n, c, mask: int = 100):
+    """heuristic.py:24-33 -> total_cost (mask 100, every value summed)."""
+    return LCM(n, c, mask_value=mask)["total"]
+
+
+def LCM_split(n, c, big_cost: int = BIG_COST):
+    """split.py:161-175 -> total_cost (mask big_cost, dummy costs not summed)."""
+    return LCM(n, c, mask_value=big_cost, sum_below=big_cost)["total"]
+
+
+def LCM_greedy_opt(n, c, threshold: int = 10, big_cost: int = BIG_COST):
+    """greedy_opt.py:61-82 -> (total_cost, allocated_supply, allocated_demand)."""
+    r = LCM(n, c, mask_value=big_cost, stop_above=threshold, sum_below=big_cost)
+    return r["total"], r["rows"].tolist(), r["cols"].tolist()
+
+
+def LCM_simulate(n, c, threshold: int = 20, big_cost: int = BIG_COST):
+    """simulate.py:76-97 -> (total_cost, allocated_supply, allocated_demand, allocated)."""
+    tot, sup, dem = LCM_greedy_opt(n, c, threshold, big_cost)
+    return tot, sup, dem, list(zip(sup, dem))
+
+
+def LCM_java(cost, big_cost: int = BIG_COST, max_non_lcm: int = 600):
+    """Simulator.java:523-549 -> (pairs, LCM_min_val)."""
+    cost = np.asarray(cost)
+    n = cost.shape[0]
+    if n == 0:
+        return [], big_cost
+    r = LCM(n, cost, mask_value=big_cost, stop_at_value=big_cost, residual_size=max_non_lcm)
+    mn = r["last_min"]
+    return list(zip(r["rows"].tolist(), r["cols"].tolist())), (big_cost if mn >= big_cost else mn)
+
+
+def find_pool(demand, dist, pool_size: int, shard: int = 0, n_shards: int = 8):
+    """One pool_n process (pool_n.c:209-238): returns (plans [m,9] int32 in the record layout of
+    pool_n.c:123-134, stats dict evaluated/feasible/kept)."""
+    eng = engine()
+    dem = _h2d_i32(np.asarray(demand, dtype=np.int32).reshape(-1, 5))
+    d = _h2d_i32(dist)
+    out, cnt, st = eng.pool_find(dem, d, pool_size, shard, n_shards)
+    m = int(cnt.item())
+    return out[:m].cpu().numpy(), {"evaluated": st.evaluated, "feasible": st.feasible, "kept": st.kept,
+                                   "rounds": st.rounds, "passes": st.passes}
+
+
+def pool_merge(shard_plans, n: int, pool_size: int):
+    """findpool.c:83-108 on shard outputs given in shard order."""
+    eng = engine()
+    parts = [np.asarray(p, dtype=np.int32).reshape(-1, POOL_REC_W) for p in shard_plans]
+    allp = np.concatenate(parts, axis=0) if parts else np.zeros((0, POOL_REC_W), np.int32)
+    if len(allp) == 0:
+        return allp
+    out, cnt = eng.pool_merge(_h2d_i32(allp), len(allp), n, pool_size)
+    return out[: int(cnt.item())].cpu().numpy()
+
+
+def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
+    """What `findpool` produces (findpool.c:122-176): all logical shards, merged in shard order."""
+    eng = engine()
+    dem_np = np.asarray(demand, dtype=np.int32).reshape(-1, 5)
+    n = dem_np.shape[0]
+    dem = _h2d_i32(dem_np)
+    d = _h2d_i32(dist)
+    cap = n // 2 + 1
+    allp = torch.empty((cap * n_shards, POOL_REC_W), dtype=torch.int32, device=eng.device)
+    total = 0
+    stats = {"evaluated": 0, "feasible": 0, "kept_per_shard": [], "rounds": 0}
+    for sh in range(n_shards):
+        out, cnt, st = eng.pool_find(dem, d, pool_size, sh, n_shards, out=allp[total: total + cap])
+        m = int(cnt.item())
+        total += m
+        stats["evaluated"] += st.evaluated
+        stats["feasible"] += st.feasible
+        stats["rounds"] += st.rounds
+        stats["kept_per_shard"].append(m)
+    merged, cnt = eng.pool_merge(allp, total, n, pool_size)
+    m = int(cnt.item())
+    stats["kept"] = m
+    return merged[:m].cpu().numpy(), stats

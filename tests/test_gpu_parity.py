@@ -1,0 +1,210 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the committed golden vectors.  Bit-exact bar for every integer result."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import assign_ref, cost_ref, gen_inputs as g, lcm_ref, pool_ref
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(arr):
+    return hashlib.sha256(np.ascontiguousarray(np.asarray(arr, dtype=np.int32)).tobytes()).hexdigest()
+
+
+# ---- K1 --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_cabs,n_cust,S,cutoff", [(3, 4, 10, None), (190, 200, 50, None), (200, 190, 50, 10),
+                                                    (1, 1, 2, None), (257, 131, 4000, None), (131, 258, 20, 5),
+                                                    (1300, 722, 50, 10), (33, 0, 5, None), (0, 33, 5, None)])
+def test_cost_matrix_matches_reference_loops(td, n_cabs, n_cust, S, cutoff):
+    rng = np.random.default_rng(n_cabs * 1000 + n_cust)
+    dist = g.stand_distances(S)
+    cabs = [(i, int(rng.integers(0, S)), int(rng.integers(0, S))) for i in range(n_cabs)]
+    dem = [(i, int(rng.integers(0, S)), int(rng.integers(0, S))) for i in range(n_cust)]
+    n, cost = td.calculate_cost(dist, dem, cabs, cutoff=cutoff)
+    n_ref, c_ref = cost_ref.calculate_cost(dist, dem, cabs, cutoff=cutoff)
+    assert n == n_ref
+    assert np.array_equal(np.asarray(cost), np.asarray(c_ref, dtype=np.int32))
+
+
+def test_cost_matrix_kat_a3_and_asymmetric_table(td):
+    d10 = g.stand_distances(10)
+    n, cost = td.calculate_cost(d10, [(0, 0, 2), (1, 0, 5), (2, 3, 1), (3, 5, 1)], [(0, 3, 3), (1, 3, 1), (2, 0, 5)], fill=16)
+    assert cost.tolist() == [[3, 3, 0, 2], [1, 1, 2, 4], [5, 5, 2, 0], [16, 16, 16, 16]]
+    rng = np.random.default_rng(9)
+    dist = rng.integers(0, 1000, (37, 37)).astype(np.int32)  # not symmetric: catches a transposed lookup
+    cabs = [(i, 0, int(rng.integers(0, 37))) for i in range(45)]
+    dem = [(i, int(rng.integers(0, 37)), 0) for i in range(51)]
+    n, cost = td.calculate_cost(dist, dem, cabs)
+    assert np.array_equal(cost, np.asarray(cost_ref.calculate_cost(dist, dem, cabs)[1], dtype=np.int32))
+    assert td.calculate_cost(dist, [], []) == (0, 0)
+    with pytest.raises(IndexError):
+        td.calculate_cost(dist, [(0, 99, 0)], [(0, 0, 1)])
+
+
+def test_cost_matrix_full_size_properties(td):
+    """config 5-B shape (20k x 20k, 4000 stands): too big for the Python loops, so check against the
+    vectorised oracle on sampled rows plus a checksum of the whole matrix."""
+    import torch
+    cab_to, cust_from = g.config5b()
+    dist = g.stand_distances(4000)
+    eng = td.engine()
+    out = eng.cost_matrix(torch.from_numpy(dist).cuda(), torch.from_numpy(cab_to).cuda(), torch.from_numpy(cust_from).cuda())
+    total = int(out.sum(dtype=torch.int64).item())
+    ref_total = int(np.abs(cab_to[:, None].astype(np.int64) - cust_from[None, :]).sum())
+    assert total == ref_total
+    rows = [0, 1, 7777, 19999]
+    got = out[rows].cpu().numpy()
+    assert np.array_equal(got, np.abs(cab_to[rows][:, None] - cust_from[None, :]))
+
+
+# ---- K3 --------------------------------------------------------------------------------------------
+def _check_lcm(td, cost, **kw):
+    n = cost.shape[0]
+    r = td.LCM(n, cost, **kw)
+    o = lcm_ref.lcm_c(cost, kw.get("mask_value", g.BIG_COST), kw.get("stop_above", 2**31 - 1),
+                      kw.get("stop_at_value", 2**31 - 1), kw.get("sum_below", 2**31 - 1), kw.get("residual_size", 0),
+                      kw.get("max_iters", -1))
+    assert r["n_pairs"] == o["n_pairs"], (r["n_pairs"], o["n_pairs"])
+    assert np.array_equal(r["rows"], o["rows"]) and np.array_equal(r["cols"], o["cols"])
+    assert r["total"] == o["total"]
+    assert r["last_min"] == o["last_min"]
+    return r
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 100, 257, 600])
+def test_lcm_heuristic_variant(td, n):
+    c = np.random.default_rng(n).integers(1, 40, (n, n)).astype(np.int32)
+    _check_lcm(td, c, mask_value=100)
+
+
+def test_lcm_all_equal_and_ties(td):
+    for n in (1, 5, 64, 130):
+        _check_lcm(td, np.full((n, n), 7, np.int32), mask_value=100)
+        _check_lcm(td, np.zeros((n, n), np.int32), mask_value=g.BIG_COST, sum_below=g.BIG_COST)
+    c = np.random.default_rng(3).integers(0, 3, (90, 90)).astype(np.int32)
+    _check_lcm(td, c, mask_value=100)
+
+
+def test_lcm_mask_is_a_value_tail(td):
+    """dummy rows of big_cost: once every free cell equals the mask the argmin re-selects masked cells
+    (SURVEY section 4 trap 4); also masks below / equal to live costs."""
+    dist, cab_to, cust_from = g.config1b()
+    n, cost = cost_ref.calculate_cost_np(dist, cab_to, cust_from)
+    r = _check_lcm(td, cost, mask_value=g.BIG_COST, sum_below=g.BIG_COST)          # split.py:161-175
+    gold = load_golden("lcm.json")["config1b_split"]
+    assert r["total"] == gold["total"] and r["rows"].tolist() == gold["rows"] and r["cols"].tolist() == gold["cols"]
+    n2, cost2 = cost_ref.calculate_cost_np(dist, cab_to[:150], cust_from)           # 50 dummy rows
+    _check_lcm(td, cost2, mask_value=g.BIG_COST, sum_below=g.BIG_COST)
+    n3, cost3 = cost_ref.calculate_cost_np(dist, cab_to, cust_from[:120], cutoff=10)  # dummy columns + cutoff holes
+    _check_lcm(td, cost3, mask_value=g.BIG_COST, sum_below=g.BIG_COST)
+    c = np.random.default_rng(8).integers(1, 40, (80, 80)).astype(np.int32)
+    for mask in (20, 1, 0, 39, 40):   # mask inside / below the live value range
+        _check_lcm(td, c, mask_value=mask)
+    c[0, :] = 50                       # row 0 expensive: exercises the (0, min masked column) branch
+    _check_lcm(td, c, mask_value=45)
+    _check_lcm(td, c, mask_value=45, max_iters=60)
+
+
+def test_lcm_threshold_and_java_variants(td):
+    dist, cab_to, cust_from = g.config1b()
+    n, cost = cost_ref.calculate_cost_np(dist, cab_to, cust_from, cutoff=10)
+    for thr in (0, 3, 10, 20):
+        _check_lcm(td, cost, mask_value=g.BIG_COST, stop_above=thr, sum_below=g.BIG_COST)  # greedy_opt.py / simulate.py
+    for res in (0, 150, 199, 1, 500):
+        _check_lcm(td, cost, mask_value=g.BIG_COST, stop_at_value=g.BIG_COST, residual_size=res)  # Simulator.java
+    pairs, mn = td.LCM_java(cost, max_non_lcm=150)
+    gp, gm = lcm_ref.lcm_java(cost, max_non_lcm=150)
+    assert pairs == gp and mn == gm
+    gj = load_golden("lcm.json")["config1b_java_res150"]
+    n0, cost0 = cost_ref.calculate_cost_np(dist, cab_to, cust_from)
+    pairs, mn = td.LCM_java(cost0, max_non_lcm=150)
+    assert [list(p) for p in pairs] == gj["pairs"] and mn == gj["lcm_min_val"]
+    tot, sup, dem = td.LCM_greedy_opt(n, cost, threshold=3)
+    assert (tot, sup, dem) == tuple(int(v) if i == 0 else v for i, v in enumerate(lcm_ref.lcm_greedy_opt(n, cost, 3)))
+    assert td.LCM_split(n, cost) == int(lcm_ref.lcm_split(n, cost)[0])
+    assert td.LCM_heuristic(50, cost[:50, :50].copy(), mask=100) == int(lcm_ref.lcm_heuristic(50, cost[:50, :50].reshape(-1))[0])
+
+
+def test_lcm_config2_golden_trace(td):
+    gold = load_golden("lcm.json")
+    r = td.LCM(2000, g.config2(), mask_value=100)
+    gh = gold["config2_heuristic"]
+    assert r["total"] == gh["total"] == 2111
+    assert sha(r["rows"]) == gh["rows_sha256"] and sha(r["cols"]) == gh["cols_sha256"]
+    Cs = g.config2_stand()
+    r = td.LCM(2000, Cs, mask_value=g.BIG_COST, sum_below=g.BIG_COST)
+    gs = gold["config2_stand_split"]
+    assert r["total"] == gs["total"] and sha(r["rows"]) == gs["rows_sha256"] and sha(r["cols"]) == gs["cols_sha256"]
+    r = td.LCM(2000, Cs, mask_value=g.BIG_COST, stop_above=10, sum_below=g.BIG_COST)
+    gt = gold["config2_stand_greedy_opt_thr10"]
+    assert (r["total"], r["n_pairs"]) == (gt["total"], gt["n_pairs"]) and sha(r["rows"]) == gt["rows_sha256"]
+
+
+# ---- K4 --------------------------------------------------------------------------------------------
+def test_pool_small_golden_all_shards(td):
+    for case in load_golden("pool_small.json"):
+        dem = np.array(case["demand"], dtype=np.int32)
+        dist = g.stand_distances(case["n_stands"])
+        k = case["pool_size"]
+        shard_plans = []
+        for s in case["shards"]:
+            plans, st = td.find_pool(dem, dist, k, s["shard"])
+            assert {q: st[q] for q in ("evaluated", "feasible", "kept")} == s["stats"], (case["label"], s["shard"])
+            assert plans.tolist() == s["plans"], (case["label"], s["shard"])
+            shard_plans.append(plans)
+        assert td.pool_merge(shard_plans, len(dem), k).tolist() == case["merged"], case["label"]
+        merged, stats = td.find_pool_all(dem, dist, k)
+        assert merged.tolist() == case["merged"]
+
+
+def test_pool_config3_722_golden(td):
+    gold = load_golden("pool722.json")
+    dem = g.pool_demand()
+    dist = g.stand_distances(50)
+    shard_plans = []
+    for s in gold["shards"]:
+        plans, st = td.find_pool(dem, dist, 4, s["shard"])
+        assert st["evaluated"] == s["stats"]["evaluated"] and st["feasible"] == s["stats"]["feasible"]
+        assert plans.tolist() == s["plans"], s["shard"]
+        shard_plans.append(plans)
+    merged = td.pool_merge(shard_plans, 722, 4)
+    assert merged.tolist() == gold["merged"]
+    assert len(merged) == 110 and int(merged[:, 8].sum()) == 1840
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_pool_random_tables_vs_oracle(td, k):
+    """asymmetric random distance table, ragged waits / losses, several shard counts"""
+    rng = np.random.default_rng(40 + k)
+    S = 23
+    dist = rng.integers(0, 9, (S, S)).astype(np.int32)
+    np.fill_diagonal(dist, 0)
+    n = 70
+    dem = np.stack([np.arange(n), rng.integers(0, S, n), rng.integers(0, S, n), rng.integers(-1, 12, n),
+                    rng.integers(0, 120, n)], axis=1).astype(np.int32)
+    for n_shards, shard in ((8, 0), (8, 7), (3, 1), (1, 0)):
+        plans, st = td.find_pool(dem, dist, k, shard, n_shards)
+        oplans, ost = pool_ref.find(dem, dist, k, shard, n_shards)
+        assert {q: st[q] for q in ost} == ost
+        assert np.array_equal(plans, oplans)
+
+
+def test_pool_edge_cases(td):
+    dist = g.stand_distances(51)
+    plans, st = td.find_pool(np.zeros((0, 5), np.int32), dist, 4, 0)
+    assert len(plans) == 0 and st["evaluated"] == 0
+    dem = g.pool_demand(3, seed=2)
+    for k in (2, 3, 4):
+        plans, st = td.find_pool(dem, dist, k, 0)
+        oplans, ost = pool_ref.find(dem, dist, k, 0)
+        assert np.array_equal(plans, oplans) and st["evaluated"] == ost["evaluated"]
+    dem = g.pool_demand(40, seed=2)
+    dem[:, 3] = 100   # waits beyond the 64-entry budget table: the explicit slack test path
+    dem[:, 4] = 300
+    plans, st = td.find_pool(dem, dist, 3, 0, 2)
+    oplans, ost = pool_ref.find(dem, dist, 3, 0, 2)
+    assert {q: st[q] for q in ost} == ost and np.array_equal(plans, oplans)
