@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the dispatch hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--components all|none]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Primary workload (BASELINE.json configs[2]): the reference's
+4-passenger pool search (pool_n.c + findpool.c) over 722 waiting customers -- 8 logical shards by
+leading customer, per-shard greedy dedup, merge -- metric "pool plans evaluated / s".  One step =
+the whole `findpool` job: 3 042 951 264 leaf plans (pool_n.c:103 count_all), checked against the
+reference's known answers every run.  At N > 1 the 8 logical shards are spread over the ranks
+(the reference's own fan-out, findpool.c:138-142), survivors are all-gathered over NCCL and merged.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events, max over
+ranks); `e2e` = the same job through the public host API with host buffers (pinned H2D + D2H
+inside the timed region); `roofline` = the dominant kernel (pool_enum_kernel) against the measured
+HBM peak using the LOGICAL bytes of SURVEY.md section 8(d) (80 B per evaluated plan + 36 B per
+feasible plan); `cpu_baseline` = the reference's own pool_n.c compiled -O3, run on the host cores
+on a bounded sample; `components` = the other kernels of the path (K2 20k x 20k time-to-optimal,
+K3 LCM/s at 2000 x 2000, K1 cost build GB/s at 20k x 20k), each with its own roofline figure.
+
+`--impl reference` times ONLY the reference CPU implementation (oracle/_ref/pool_n_big64, the
+unmodified pool_n.c with its shard count raised so that a step is a bounded 1/8 sample).
+"""
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POOL_N = 722
+POOL_K = 4
+POOL_STANDS = 50
+LOGICAL_B_PER_PLAN = 80      # 4 customers x the 5-int32 demand record (pool_n.c:20)
+LOGICAL_B_PER_FEASIBLE = 36  # one pool[] record (pool_n.c:26)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        mhz = [int(s[0]) for s in self.samples if s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference CPU arm (also the cpu_baseline of our arm)
+# ---------------------------------------------------------------------------------------------------
+def _run_ref_slice(args):
+    exe, csv_path, n, k, t = args
+    with tempfile.TemporaryDirectory() as td:
+        res = subprocess.run([exe, str(k), str(t), csv_path, str(n), os.path.join(td, "out.csv")], cwd=td,
+                             capture_output=True, text=True)
+    m = re.search(r"Count ALL: (\d+)", res.stdout)
+    return int(m.group(1)) if m else 0
+
+
+def reference_sample(n_slices=8):
+    """One bounded sample of config 3 on the host cores: slices 0..n_slices-1 of the 64-way shard rule
+    of the UNMODIFIED pool_n.c (oracle/_ref/pool_n_big64), one process per slice, all at once (the
+    way findpool.c:138-142 fans out).  Returns (plans, seconds, processes)."""
+    from oracle import gen_inputs as g
+    exe = os.path.join(ROOT, "oracle", "_ref", "pool_n_big64")
+    if not os.path.exists(exe):
+        from oracle import _clib
+        _clib.build_ref()
+    if not os.path.exists(exe):
+        raise FileNotFoundError(exe)
+    dem = g.pool_demand(POOL_N)
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as f:
+        f.write(g.demand_csv(dem))
+        csv_path = f.name
+    procs = min(n_slices, os.cpu_count() or 1)
+    try:
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(procs) as ex:
+            counts = list(ex.map(_run_ref_slice, [(exe, csv_path, POOL_N, POOL_K, t) for t in range(n_slices)]))
+        dt = time.perf_counter() - t0
+    finally:
+        os.unlink(csv_path)
+    return sum(counts), dt, procs
+
+
+SAMPLE_TEXT = "leading customers 0..95 of 722 (slices 0-7 of a 64-way pool_n.c shard rule, one process per slice)"
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    try:
+        for _ in range(args.warmup):
+            reference_sample()
+        t_tot, plans_tot, procs = 0.0, 0, 1
+        for _ in range(args.steps):
+            plans, dt, procs = reference_sample()
+            t_tot += dt
+            plans_tot += plans
+        val = plans_tot / t_tot
+        line = {"impl": "reference", "metric": "pool plans evaluated per second", "value": val, "unit": "plans/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "pool_n 4-passenger pool search, 722 customers (SURVEY 8(d) config 3)",
+                           "pool_size": POOL_K, "customers": POOL_N, "stands": POOL_STANDS, "sample": SAMPLE_TEXT},
+                "cpu_baseline": {"value": val, "unit": "plans/s", "cores": procs, "kind": "reference", "sample": SAMPLE_TEXT},
+                "e2e": {"value": val, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+    except Exception as e:  # the oracle always exists; report instead of crashing the driver
+        line = {"impl": "reference", "unavailable": "%s: %s" % (type(e).__name__, e)}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--components", default="all", choices=["all", "none"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import gen_inputs as g       # inputs + known answers (checker only)
+    from taxidispatcher_b200 import _lib, dispatch, parallel
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.lib()
+    eng = dispatch.Engine()
+    dev = eng.device
+    hbm_peak, peak_src = measured_peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    # ---- pool job, device resident ---------------------------------------------------------------
+    dem_np = g.pool_demand(POOL_N)
+    dist_np = g.stand_distances(POOL_STANDS)
+    dem_d = torch.from_numpy(dem_np).to(dev)
+    dist_d = torch.from_numpy(dist_np).to(dev)
+    my_shards = parallel.shards_for_rank(rank, world)
+    slots = (8 + world - 1) // world
+    cap = POOL_N // 2 + 1
+    slot_plans = torch.zeros((slots, cap, 9), dtype=torch.int32, device=dev)
+    slot_counts = torch.zeros(slots, dtype=torch.int32, device=dev)
+    all_plans = torch.zeros((world * slots, cap, 9), dtype=torch.int32, device=dev)
+    all_counts = torch.zeros(world * slots, dtype=torch.int32, device=dev)
+    slot_shard = torch.tensor([r + s * world if r + s * world < 8 else 0 for r in range(world) for s in range(slots)],
+                              dtype=torch.int32, device=dev)
+
+    def pool_step(want_stats=False):
+        stats = []
+        slot_counts.zero_()
+        for s, sh in enumerate(my_shards):
+            _, _, st = eng.pool_find(dem_d, dist_d, POOL_K, sh, 8, out=slot_plans[s], want_stats=want_stats,
+                                     cnt_out=slot_counts[s:s + 1])
+            stats.append(st)
+        if world > 1:
+            dist.all_gather_into_tensor(all_plans, slot_plans)
+            dist.all_gather_into_tensor(all_counts, slot_counts)
+            src_p, src_c = all_plans, all_counts
+        else:
+            src_p, src_c = slot_plans, slot_counts
+        merged = cnt = None
+        if rank == 0:
+            merged, cnt = eng.pool_merge_padded(src_p, src_c, slot_shard, POOL_N, POOL_K)
+        return merged, cnt, stats
+
+    # correctness gate (also the first warm-up): counts and merged result must equal the known answers
+    merged, cnt, stats = pool_step(want_stats=True)
+    torch.cuda.synchronize()
+    ev_local = sum(int(s.evaluated) for s in stats)
+    fe_local = sum(int(s.feasible) for s in stats)
+    for st, sh in zip(stats, my_shards):
+        assert int(st.evaluated) == g.POOL722_EVALUATED[sh] and int(st.feasible) == g.POOL722_FEASIBLE[sh], \
+            "pool counts differ from the reference's known answers (shard %d)" % sh
+    tot = torch.tensor([ev_local, fe_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    plans_per_step, feas_per_step = int(tot[0]), int(tot[1])
+    if rank == 0:
+        m = merged[: int(cnt.item())].cpu().numpy()
+        assert len(m) == 110 and int(m[:, 8].sum()) == 1840, "merged pool result differs from KAT P2"
+        golden = json.load(open(os.path.join(ROOT, "tests", "golden", "pool722.json")))["merged"]
+        assert m.tolist() == golden, "merged pool result differs from tests/golden/pool722.json"
+    for _ in range(args.warmup - 1):
+        pool_step()
+    barrier()
+
+    lib.td_prof_reset()
+    lib.td_prof_enable(1)
+    lib.td_launch_count_reset()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        for i in range(args.steps):
+            flush_l2()
+            ev0[i].record()
+            pool_step()
+            ev1[i].record()
+        barrier()
+    launches = int(lib.td_launch_count())
+    lib.td_prof_enable(0)
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = plans_per_step * args.steps / (total_ms * 1e-3)
+
+    # dominant kernel: pool_enum (per-launch average over the timed region, this rank's shards)
+    import ctypes
+    pm, pc = ctypes.c_double(), ctypes.c_int64()
+    lib.td_prof_read(_lib.PROF_POOL_ENUM, ctypes.byref(pm), ctypes.byref(pc))
+    enum_ms, enum_n = pm.value, pc.value
+    lib.td_prof_read(_lib.PROF_POOL_SELECT, ctypes.byref(pm), ctypes.byref(pc))
+    sel_ms = pm.value
+    lib.td_prof_reset()
+    bytes_per_launch = (LOGICAL_B_PER_PLAN * ev_local + LOGICAL_B_PER_FEASIBLE * fe_local) / max(len(my_shards), 1)
+    avg_enum_ms = enum_ms / max(enum_n, 1)
+    achieved = bytes_per_launch / (avg_enum_ms * 1e-3) / 1e9 if avg_enum_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("pool_enum_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "pool_enum_kernel<4>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_model": "logical: 80 B per evaluated plan + 36 B per feasible plan (SURVEY 8(d)); the kernel is "
+                               "INT32-issue / shared-memory bound, compulsory HBM traffic is ~0.4 B per plan",
+                "avg_launch_ms": avg_enum_ms, "launches": enum_n, "share_of_step": enum_ms / max(sum(step_ms), 1e-9),
+                "pool_select_share_of_step": sel_ms / max(sum(step_ms), 1e-9)}
+
+    # ---- e2e: the public host API with host buffers ----------------------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        if world == 1:
+            return dispatch.find_pool_all(dem_np, dist_np, POOL_K)
+        return parallel.find_pool_sharded(dem_np, dist_np, POOL_K)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        m_e2e, st_e2e = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+    if rank == 0:
+        assert len(m_e2e) == 110 and st_e2e["evaluated"] == plans_per_step
+    h2d = dem_np.nbytes + dist_np.nbytes
+    d2h = (len(my_shards) + 1) * 4 + int(110 * 36) + len(my_shards) * 32
+    e2e = {"value": plans_per_step * e2e_steps / e2e_s, "unit": "plans/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "api": "taxidispatcher_b200.find_pool_all(demand, dist, 4)" if world == 1 else
+                  "taxidispatcher_b200.parallel.find_pool_sharded(demand, dist, 4)"}
+
+    # ---- CPU baseline + the other kernels (rank 0, N = 1 only) -----------------------------------
+    cpu_baseline = None
+    components = {}
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            try:
+                plans, dt, procs = reference_sample()
+                plans2, dt2, _ = reference_sample()
+                cpu_baseline = {"value": (plans + plans2) / (dt + dt2), "unit": "plans/s", "cores": procs, "kind": "reference",
+                                "sample": SAMPLE_TEXT + ", run twice", "host_cores": os.cpu_count()}
+            except Exception as e:
+                cpu_baseline = {"value": None, "unit": "plans/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+        if args.components == "all":
+            try:
+                components = run_components(torch, np, g, eng, lib, _lib, dispatch, hbm_peak, flush_l2)
+            except Exception as e:
+                components = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": "pool plans evaluated per second", "value": value, "unit": "plans/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": "pool_n 4-passenger pool search, 722 customers, 8 logical shards + merge "
+                                       "(BASELINE.json configs[2], SURVEY 8(d) config 3)",
+                           "pool_size": POOL_K, "customers": POOL_N, "stands": POOL_STANDS, "max_wait": 3, "max_loss_pct": 1,
+                           "plans_per_step": plans_per_step, "feasible_per_step": feas_per_step,
+                           "parallelism": "logical shards round-robin over %d rank(s), all_gather + merge" % world,
+                           "l2": "256 MiB write between steps (untimed); inputs are 15 KB"},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "components": components}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_components(torch, np, g, eng, lib, _lib, dispatch, hbm_peak, flush_l2):
+    """K1 / K2 / K3 on their BASELINE.json shapes (config 5 and config 2), device timings with CUDA events."""
+    import ctypes
+    out = {}
+
+    def timed(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return ms, r
+
+    # K1: 20k x 20k cost build, 4000 stands (config 5-B)
+    n = 20000
+    cab_to, cust_from = g.config5b()
+    dist_d = torch.from_numpy(g.stand_distances(4000)).cuda()
+    cab_d, cust_d = torch.from_numpy(cab_to).cuda(), torch.from_numpy(cust_from).cuda()
+    cost_b = torch.empty((n, n), dtype=torch.int32, device="cuda")
+    ms, _ = timed(lambda: eng.cost_matrix(dist_d, cab_d, cust_d, out=cost_b), reps=5, warm=3)
+    k1_bytes = 4 * n * n + 4 * 2 * n + 4 * 4000 * 4000
+    best = min(ms)
+    out["cost_matrix_20k"] = {"ms": statistics.median(ms), "ms_best": best, "bytes": k1_bytes,
+                              "roofline": {"bound": "hbm", "achieved": k1_bytes / (statistics.median(ms) * 1e-3) / 1e9,
+                                           "peak": hbm_peak, "unit": "GB/s",
+                                           "frac": k1_bytes / (statistics.median(ms) * 1e-3) / 1e9 / hbm_peak}}
+    # K2: exact 20k x 20k, config 5-B (stand derived) and 5-A (U[1,39])
+    for name, cost in (("assign_20k_5B_stand", cost_b), ("assign_20k_5A_uniform", None)):
+        if cost is None:
+            cost = torch.from_numpy(g.config5a()).cuda()
+        res = {}
+
+        def solve():
+            col, obj, _, st = eng.assign(cost, want_stats=True)
+            res["st"], res["obj"] = st, int(obj.item())
+        ms, _ = timed(solve, reps=2, warm=1)
+        st = res["st"]
+        sec = statistics.median(ms) * 1e-3
+        swept = 4.0 * n * st.rows_scanned
+        out[name] = {"time_to_optimal_s": sec, "objective": res["obj"], "phases": st.phases, "levels": st.search_steps,
+                     "rows_scanned": st.rows_scanned, "sweeps": st.rows_scanned / n,
+                     "roofline": {"bound": "hbm", "achieved": swept / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": swept / sec / 1e9 / hbm_peak, "bytes_model": "4n bytes per cost row relaxed"}}
+        # e2e: host matrix in pinned memory -> device -> solve -> assignment back on the host
+        if name == "assign_20k_5B_stand":
+            host = cost.cpu().pin_memory()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dcost = host.to("cuda", non_blocking=True)
+            col, obj, _, _ = eng.assign(dcost)
+            col_h = col.cpu()
+            obj_h = int(obj.item())
+            out[name]["e2e_s"] = time.perf_counter() - t0
+            out[name]["e2e_h2d_bytes"] = host.numel() * 4
+            assert obj_h == res["obj"]
+            del host, dcost
+        if name == "assign_20k_5A_uniform":
+            del cost
+    # K3: LCM on 2000 x 2000 (config 2), heuristic.py variant
+    c2 = torch.from_numpy(g.config2()).cuda()
+    ms, r = timed(lambda: eng.lcm(c2, 100), reps=10, warm=3)
+    hv = eng.lcm_host_view(*r)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "lcm.json")))["config2_heuristic"]
+    assert hv["total"] == golden["total"], "LCM total differs from the golden trace"
+    med = statistics.median(ms)
+    out["lcm_2000"] = {"ms": med, "lcm_per_s": 1e3 / med, "total": hv["total"],
+                       "roofline": {"bound": "hbm", "achieved": 4 * 2000 * 2000 / (med * 1e-3) / 1e9, "peak": hbm_peak,
+                                    "unit": "GB/s", "frac": 4 * 2000 * 2000 / (med * 1e-3) / 1e9 / hbm_peak,
+                                    "bytes_model": "4 n^2 (each cost read once); L2-resident and sync-latency bound"}}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -58,6 +58,19 @@ int td_device_count(void);
 int64_t td_launch_count(void);
 void td_launch_count_reset(void);
 
+/* Optional per-kernel device timing (CUDA events recorded on the launching stream around the
+ * dominant kernel of each operation).  Off by default; used by bench.py for the roofline figure. */
+#define TD_PROF_COST 0        /* cost_matrix_kernel */
+#define TD_PROF_LCM 1         /* lcm_rounds_kernel */
+#define TD_PROF_ASSIGN 2      /* assign_kernel */
+#define TD_PROF_POOL_ENUM 3   /* pool_enum_kernel */
+#define TD_PROF_POOL_SELECT 4 /* pool_select_kernel */
+#define TD_PROF_KINDS 5
+void td_prof_enable(int on);
+void td_prof_reset(void);
+/* waits for the recorded events; total_ms = sum of durations, count = launches */
+int td_prof_read(int kind, double *total_ms, int64_t *count);
+
 /* ------------------------------------------------------------------------------------------
  * K1  cost matrix            replaces calculate_cost(distances, demand, cabs)
  *     split.py:123-136 (= greedy_opt.py:86-99), cutoff variant simulate.py:17-33 and
@@ -154,6 +167,15 @@ size_t td_pool_merge_workspace_bytes(int total_plans, int n);
 int td_pool_merge(const int32_t *shard_plans /* total x 9 */, int total_plans, int n, int pool_size,
                   int32_t *plans_out /* total x 9 */, int32_t *n_plans_out /* 1 */,
                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same merge on the fixed-capacity layout that travels through the gather: n_slots slots of `cap`
+ * rows each, slot_counts[slot] valid rows per slot (device), slot_shard[slot] = logical shard of the
+ * slot (device, NULL: slot index); concatenation order = shard order.  No host round trip. */
+int td_pool_merge_padded(const int32_t *slot_plans, const int32_t *slot_counts, const int32_t *slot_shard,
+                         int n_slots, int cap, int n, int pool_size,
+                         int32_t *plans_out /* n_slots*cap x 9 */, int32_t *n_plans_out /* 1 */,
+                         void *workspace, size_t workspace_bytes /* td_pool_merge_workspace_bytes(n_slots*cap, n) */,
+                         void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer twins (allocate, copy, run, copy back).  Same semantics as above.

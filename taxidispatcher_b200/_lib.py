@@ -18,6 +18,7 @@ TD_ERR_NOT_CONVERGED = -6
 INT32_MAX = 2**31 - 1
 BIG_COST = 250000
 POOL_REC_W = 9
+PROF_COST, PROF_LCM, PROF_ASSIGN, PROF_POOL_ENUM, PROF_POOL_SELECT = range(5)
 
 c_i32p = ctypes.c_void_p
 c_vp = ctypes.c_void_p
@@ -54,6 +55,9 @@ _SIGNATURES = {
     "td_device_count": (_I, []),
     "td_launch_count": (ctypes.c_int64, []),
     "td_launch_count_reset": (None, []),
+    "td_prof_enable": (None, [_I]),
+    "td_prof_reset": (None, []),
+    "td_prof_read": (_I, [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "td_cost_matrix": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp]),
     "td_lcm_workspace_bytes": (ctypes.c_size_t, [_I]),
     "td_lcm": (_I, [c_vp, _I, ctypes.POINTER(LcmParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
@@ -64,6 +68,7 @@ _SIGNATURES = {
                           c_vp, ctypes.c_size_t, ctypes.c_int64, c_vp]),
     "td_pool_merge_workspace_bytes": (ctypes.c_size_t, [_I, _I]),
     "td_pool_merge": (_I, [c_vp, _I, _I, _I, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "td_pool_merge_padded": (_I, [c_vp, c_vp, c_vp, _I, _I, _I, _I, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "tdh_cost_matrix": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, c_vp]),
     "tdh_lcm": (_I, [c_vp, _I, ctypes.POINTER(LcmParams), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tdh_assign_exact": (_I, [c_vp, _I, c_vp, c_vp, c_vp, ctypes.POINTER(AssignStats)]),

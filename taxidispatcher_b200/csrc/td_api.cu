@@ -41,6 +41,25 @@ int device_sm_count() {
     return sms;
 }
 
+// ---- optional per-kernel timing ------------------------------------------------------------------
+struct ProfPair { cudaEvent_t a, b; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfPair> g_prof[TD_PROF_KINDS];
+static thread_local std::vector<ProfPair> g_prof_pool;
+
+ProfScope::ProfScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_), slot(nullptr) {
+    if (!g_prof_on || kind < 0 || kind >= TD_PROF_KINDS) return;
+    ProfPair p;
+    if (!g_prof_pool.empty()) { p = g_prof_pool.back(); g_prof_pool.pop_back(); }
+    else if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+    cudaEventRecord(p.a, st);
+    g_prof[kind].push_back(p);
+    slot = &g_prof[kind];
+}
+ProfScope::~ProfScope() {
+    if (slot) cudaEventRecord(g_prof[kind].back().b, st);
+}
+
 // RAII device buffer for the tdh_* twins
 struct DevBuf {
     void *p = nullptr;
@@ -70,6 +89,28 @@ extern "C" int td_device_count(void) {
     int c = 0;
     if (cudaGetDeviceCount(&c) != cudaSuccess || c <= 0) { cudaGetLastError(); return TD_ERR_NO_DEVICE; }
     return c;
+}
+extern "C" void td_prof_enable(int on) { td::g_prof_on = on != 0; }
+extern "C" void td_prof_reset(void) {
+    for (int k = 0; k < TD_PROF_KINDS; ++k) {
+        for (auto &p : td::g_prof[k]) td::g_prof_pool.push_back(p);
+        td::g_prof[k].clear();
+    }
+}
+extern "C" int td_prof_read(int kind, double *total_ms, int64_t *count) {
+    if (kind < 0 || kind >= TD_PROF_KINDS || !total_ms || !count) return TD_ERR_INVALID;
+    double tot = 0;
+    for (auto &p : td::g_prof[kind]) {
+        cudaError_t e = cudaEventSynchronize(p.b);
+        if (e != cudaSuccess) { td::set_cuda_error(e, "cudaEventSynchronize"); return TD_ERR_CUDA; }
+        float ms = 0;
+        e = cudaEventElapsedTime(&ms, p.a, p.b);
+        if (e != cudaSuccess) { td::set_cuda_error(e, "cudaEventElapsedTime"); return TD_ERR_CUDA; }
+        tot += ms;
+    }
+    *total_ms = tot;
+    *count = int64_t(td::g_prof[kind].size());
+    return TD_OK;
 }
 extern "C" int64_t td_launch_count(void) { return td::g_launches; }
 extern "C" void td_launch_count_reset(void) { td::g_launches = 0; }

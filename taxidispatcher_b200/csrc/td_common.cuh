@@ -16,6 +16,13 @@ void count_launch(int n = 1);
 int device_sm_count();
 bool have_device();
 
+// RAII: records a start/stop event pair around a launch when profiling is enabled (td_prof_enable)
+struct ProfScope {
+    int kind; cudaStream_t st; void *slot;
+    ProfScope(int kind, cudaStream_t st);
+    ~ProfScope();
+};
+
 #define TD_CUDA_TRY(expr)                                   \
     do {                                                    \
         cudaError_t _e = (expr);                            \

@@ -91,6 +91,7 @@ extern "C" int td_cost_matrix(const int32_t *dist, int n_stands, const int32_t *
     per_sm = per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm);
     int grid = sms * per_sm;
     if (grid > n) grid = n;
+    td::ProfScope prof(TD_PROF_COST, st);
     if (row_in_smem) {
         TD_CUDA_TRY(cudaFuncSetAttribute(td::cost_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
         td::cost_matrix_kernel<true><<<grid, td::kCostThreads, smem, st>>>(dist, n_stands, cab_to, n_cabs, cust_from, n_cust,

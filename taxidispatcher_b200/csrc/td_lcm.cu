@@ -384,7 +384,10 @@ extern "C" int td_lcm(const int32_t *cost, int n, const td_lcm_params *params, i
     const int32_t *costT = w.costT;
     void *args[] = {(void *)&cost, (void *)&costT, (void *)&n, (void *)&prm, (void *)&w.rowkey, (void *)&w.colkey,
                     (void *)&w.rowfree, (void *)&w.colfree, (void *)&w.picked, (void *)&w.ctrl};
-    TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lcm_rounds_kernel, dim3(grid), dim3(kLcmThreads), args, 0, st));
+    {
+        ProfScope prof(TD_PROF_LCM, st);
+        TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lcm_rounds_kernel, dim3(grid), dim3(kLcmThreads), args, 0, st));
+    }
     count_launch();
 
     lcm_rank_sort_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.picked, w.sorted, w.ctrl);

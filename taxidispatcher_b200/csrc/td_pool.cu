@@ -542,24 +542,32 @@ pool_emit_kernel(const PoolRec *__restrict__ kept, const PoolCtrl *ctrl, int K, 
 }
 
 // ---- merge (findpool.c:83-108) ---------------------------------------------------------------
-// total <= n_shards * n / K rows; runs in one CTA: stable order by column 8 (or concatenation
+// total <= n_shards * (n/2+1) rows; runs in one CTA: stable order by column 8 (or concatenation
 // order for K < 4, see header), then the same dominance rounds on the tiny list.
+// Padded form: `counts` != NULL -> row i belongs to slot i / cap and is valid iff i % cap < counts[slot];
+// slot_shard[slot] gives the logical shard of the slot (concatenation order = shard order).
 __global__ void __launch_bounds__(1024)
-pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, int32_t *order_key /* total */,
-                  int32_t *owner /* n */, uint8_t *state /* total: 0 live, 1 kept, 2 dead */, int32_t *plans_out,
-                  int32_t *n_plans_out) {
+pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, const int32_t *__restrict__ counts, int cap,
+                  const int32_t *__restrict__ slot_shard, int32_t *order_key /* total */, int32_t *owner /* n */,
+                  uint8_t *state /* total: 0 live, 1 kept, 2 dead */, int32_t *plans_out, int32_t *n_plans_out) {
     __shared__ int s_live;
     const int tid = threadIdx.x;
+    auto valid = [&](int i) -> bool { return !counts || (i % cap) < counts[i / cap]; };
+    auto concat_pos = [&](int i) -> long long {
+        if (!counts) return i;
+        const int slot = i / cap;
+        return (long long)(slot_shard ? slot_shard[slot] : slot) * cap + (i % cap);
+    };
     // position of every row in the scan order: (cost, concatenation index) for K == 4, index otherwise
     for (int i = tid; i < total; i += blockDim.x) {
-        int pos = i;
-        if (K == TD_POOL_MAX_IN_POOL) {
-            const int ci = plans[size_t(i) * TD_POOL_REC_W + 8];
-            pos = 0;
-            for (int j = 0; j < total; ++j) {
-                const int cj = plans[size_t(j) * TD_POOL_REC_W + 8];
-                pos += (cj < ci) || (cj == ci && j < i);
-            }
+        if (!valid(i)) { state[i] = 2; order_key[i] = INT_MAX; continue; }
+        const int ci = K == TD_POOL_MAX_IN_POOL ? plans[size_t(i) * TD_POOL_REC_W + 8] : 0;
+        const long long pi = concat_pos(i);
+        int pos = 0;
+        for (int j = 0; j < total; ++j) {
+            if (!valid(j)) continue;
+            const int cj = K == TD_POOL_MAX_IN_POOL ? plans[size_t(j) * TD_POOL_REC_W + 8] : 0;
+            pos += (cj < ci) || (cj == ci && concat_pos(j) < pi);
         }
         order_key[i] = pos;
         state[i] = 0;
@@ -711,7 +719,11 @@ extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, i
     ea.cap = unsigned(rec_cap64);
     const int sms = device_sm_count();
     const int grid = sms * 4;
-    int rc = pool_size == 4 ? launch_enum<4>(ea, grid, st) : pool_size == 3 ? launch_enum<3>(ea, grid, st) : launch_enum<2>(ea, grid, st);
+    int rc;
+    {
+        ProfScope prof(TD_PROF_POOL_ENUM, st);
+        rc = pool_size == 4 ? launch_enum<4>(ea, grid, st) : pool_size == 3 ? launch_enum<3>(ea, grid, st) : launch_enum<2>(ea, grid, st);
+    }
     if (rc != TD_OK) return rc;
 
     SelArgs sa;
@@ -723,7 +735,10 @@ extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, i
     if (per_sm < 1) return TD_ERR_CUDA;
     per_sm = per_sm > 2 ? 2 : per_sm;
     void *sargs[] = {(void *)&sa};
-    TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)pool_select_kernel, dim3(sms * per_sm), dim3(kSelThreads), sargs, 0, st));
+    {
+        ProfScope prof(TD_PROF_POOL_SELECT, st);
+        TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)pool_select_kernel, dim3(sms * per_sm), dim3(kSelThreads), sargs, 0, st));
+    }
     count_launch();
     pool_emit_kernel<<<1, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, plans_out, cap, n_plans_out);
     TD_LAUNCH_CHECK();
@@ -764,7 +779,31 @@ extern "C" int td_pool_merge(const int32_t *shard_plans, int total_plans, int n,
     int32_t *order_key = c.take<int32_t>(total_plans);
     int32_t *owner = c.take<int32_t>(n > 0 ? n : 1);
     uint8_t *state = c.take<uint8_t>(total_plans);
-    pool_merge_kernel<<<1, 1024, 0, st>>>(shard_plans, total_plans, n, pool_size, order_key, owner, state, plans_out, n_plans_out);
+    pool_merge_kernel<<<1, 1024, 0, st>>>(shard_plans, total_plans, n, pool_size, nullptr, 1, nullptr, order_key, owner, state,
+                                          plans_out, n_plans_out);
+    TD_LAUNCH_CHECK();
+    return TD_OK;
+}
+
+extern "C" int td_pool_merge_padded(const int32_t *slot_plans, const int32_t *slot_counts, const int32_t *slot_shard,
+                                    int n_slots, int cap, int n, int pool_size, int32_t *plans_out, int32_t *n_plans_out,
+                                    void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace td;
+    if (n_slots < 0 || cap < 1 || n < 0 || pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || !n_plans_out) return TD_ERR_INVALID;
+    if (!have_device()) return TD_ERR_NO_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total64 = (long long)n_slots * cap;
+    if (total64 > (1 << 24)) return TD_ERR_INVALID;
+    const int total = int(total64);
+    if (total == 0) { TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st)); return TD_OK; }
+    if (!slot_plans || !slot_counts || !plans_out || !workspace) return TD_ERR_INVALID;
+    if (workspace_bytes < td_pool_merge_workspace_bytes(total, n)) return TD_ERR_WORKSPACE;
+    Carver c(workspace);
+    int32_t *order_key = c.take<int32_t>(total);
+    int32_t *owner = c.take<int32_t>(n > 0 ? n : 1);
+    uint8_t *state = c.take<uint8_t>(total);
+    pool_merge_kernel<<<1, 1024, 0, st>>>(slot_plans, total, n, pool_size, slot_counts, cap, slot_shard, order_key, owner, state,
+                                          plans_out, n_plans_out);
     TD_LAUNCH_CHECK();
     return TD_OK;
 }

@@ -128,13 +128,16 @@ class Engine:
 
     # -- K4 ---------------------------------------------------------------------------------------
     def pool_find(self, demand: torch.Tensor, dist: torch.Tensor, pool_size: int, shard: int = 0, n_shards: int = 8,
-                  max_feasible: Optional[int] = None, out: Optional[torch.Tensor] = None, want_stats: bool = True):
+                  max_feasible: Optional[int] = None, out: Optional[torch.Tensor] = None, want_stats: bool = True,
+                  cnt_out: Optional[torch.Tensor] = None):
+        """out: [cap, 9] int32 device rows (cap >= n // pool_size); cnt_out: 1-element int32 device view that
+        receives the number of surviving plans (-1: the record list overflowed, only when want_stats=False)."""
         n = int(demand.shape[0])
         n_stands = int(dist.shape[0])
         cap = n // 2 + 1
         if out is None:
             out = torch.empty((cap, POOL_REC_W), dtype=torch.int32, device=self.device)
-        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        cnt = cnt_out if cnt_out is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
         mf = int(max_feasible) if max_feasible is not None else self._ws.get(("pool_mf", n, pool_size), 1 << 21)
         for _ in range(8):
             nbytes = self.lib.td_pool_workspace_bytes(n, n_stands, pool_size, mf)
@@ -159,6 +162,21 @@ class Engine:
         rc = self.lib.td_pool_merge(_ptr(shard_plans), total, n, pool_size, _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(),
                                     _stream())
         check(rc, "td_pool_merge")
+        return out, cnt
+
+
+    def pool_merge_padded(self, slot_plans: torch.Tensor, slot_counts: torch.Tensor, slot_shard: Optional[torch.Tensor],
+                          n: int, pool_size: int):
+        """slot_plans [n_slots, cap, 9], slot_counts [n_slots] (device).  Returns (plans, count) device tensors."""
+        n_slots, cap = int(slot_plans.shape[0]), int(slot_plans.shape[1])
+        total = n_slots * cap
+        out = torch.empty((max(total, 1), POOL_REC_W), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nbytes = self.lib.td_pool_merge_workspace_bytes(total, n)
+        ws = self._workspace(("merge", total, n), nbytes)
+        rc = self.lib.td_pool_merge_padded(_ptr(slot_plans), _ptr(slot_counts), _ptr(slot_shard), n_slots, cap, n, pool_size,
+                                           _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(), _stream())
+        check(rc, "td_pool_merge_padded")
         return out, cnt
 
 

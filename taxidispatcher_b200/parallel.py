@@ -1,0 +1,113 @@
+"""Multi-GPU partitioning of the parts of the hot path that shard naturally.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).  No data-path
+collective inside any kernel -- the only exchange is the reference's own: gather the per-shard
+survivors, then re-run the greedy scan on the concatenation (findpool.c:149-172).
+
+  pool      the 8 LOGICAL shards of pool_n.c:226-229 are kept whatever the GPU count (the result
+            depends on them: each shard dedups before the merge); rank r runs logical shards
+            r, r+W, r+2W, ...; one all_gather of fixed-capacity survivor buffers; every rank (or
+            rank 0 only) merges in shard order.
+  cost      contiguous cab-row blocks per rank (rows_for_rank); no exchange.
+  assign    independent instances (split.py ranges, per-minute batches) round-robin over ranks.
+  LCM       does not shard (sequential chain): replicas only.
+
+`compute_shard` / `merge` are injected so that the host logic can be exercised on CPU with the
+oracle standing in for the device (tests only); the product default is the CUDA engine.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REC_W = 9
+REF_SHARDS = 8  # pool_n.c:13 MAX_THREAD
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shards_for_rank(rank: int, world_size: int, n_shards: int = REF_SHARDS) -> List[int]:
+    """Logical shards owned by `rank` (round-robin, so that 8 shards balance over 1/2/4/8 ranks)."""
+    return list(range(rank, n_shards, world_size))
+
+
+def rows_for_rank(n_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous cab-row block [lo, hi) of the cost matrix for `rank` (balanced to within one row)."""
+    base, rem = divmod(n_rows, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def instances_for_rank(n_instances: int, rank: int, world_size: int) -> List[int]:
+    return list(range(rank, n_instances, world_size))
+
+
+def _device_for_collectives() -> torch.device:
+    backend = dist.get_backend() if dist.is_initialized() else "gloo"
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def gather_shard_plans(local: Sequence[Tuple[int, np.ndarray]], n: int, n_shards: int = REF_SHARDS) -> List[np.ndarray]:
+    """local: [(shard index, plans [m,9])] computed by this rank.  Returns the plans of ALL logical
+    shards in shard order on every rank.  One all_gather of a fixed-capacity int32 buffer:
+    per shard a count followed by cap x 9 ints, cap = n // 2 + 1 (survivors are customer-disjoint)."""
+    rank, w = world()
+    cap = n // 2 + 1
+    slots = (n_shards + w - 1) // w          # shards per rank, padded
+    stride = 2 + cap * REC_W                  # [shard id, count, rows...]
+    buf = np.full((slots, stride), -1, dtype=np.int32)
+    for slot, (sh, plans) in enumerate(local):
+        plans = np.asarray(plans, dtype=np.int32).reshape(-1, REC_W)
+        if len(plans) > cap:
+            raise ValueError("shard %d returned %d plans, capacity %d" % (sh, len(plans), cap))
+        buf[slot, 0] = sh
+        buf[slot, 1] = len(plans)
+        buf[slot, 2: 2 + plans.size] = plans.reshape(-1)
+    if w == 1:
+        gathered = [buf]
+    else:
+        dev = _device_for_collectives()
+        mine = torch.from_numpy(buf).to(dev)
+        outs = [torch.empty_like(mine) for _ in range(w)]
+        dist.all_gather(outs, mine)
+        gathered = [o.cpu().numpy() for o in outs]
+    by_shard = {}
+    for g in gathered:
+        for row in g:
+            if row[0] >= 0:
+                by_shard[int(row[0])] = row[2: 2 + int(row[1]) * REC_W].reshape(-1, REC_W).copy()
+    return [by_shard[s] for s in range(n_shards)]
+
+
+def find_pool_sharded(demand, dist_table, pool_size: int, n_shards: int = REF_SHARDS,
+                      compute_shard: Optional[Callable] = None, merge: Optional[Callable] = None):
+    """`findpool` over the ranks of the current process group: returns (merged plans, stats) on every
+    rank.  stats carry the sums over all logical shards (evaluated, feasible) and kept_per_shard."""
+    if compute_shard is None or merge is None:
+        from . import dispatch
+        compute_shard = compute_shard or dispatch.find_pool
+        merge = merge or dispatch.pool_merge
+    rank, w = world()
+    dem = np.asarray(demand, dtype=np.int32).reshape(-1, 5)
+    n = dem.shape[0]
+    local = []
+    ev = fe = 0
+    for sh in shards_for_rank(rank, w, n_shards):
+        plans, st = compute_shard(dem, dist_table, pool_size, sh, n_shards)
+        local.append((sh, plans))
+        ev += int(st["evaluated"])
+        fe += int(st["feasible"])
+    all_plans = gather_shard_plans(local, n, n_shards)
+    if w > 1:
+        t = torch.tensor([ev, fe], dtype=torch.int64, device=_device_for_collectives())
+        dist.all_reduce(t)
+        ev, fe = int(t[0]), int(t[1])
+    merged = merge(all_plans, n, pool_size)
+    return merged, {"evaluated": ev, "feasible": fe, "kept_per_shard": [len(p) for p in all_plans], "kept": len(merged)}

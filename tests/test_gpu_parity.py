@@ -208,3 +208,74 @@ def test_pool_edge_cases(td):
     plans, st = td.find_pool(dem, dist, 3, 0, 2)
     oplans, ost = pool_ref.find(dem, dist, 3, 0, 2)
     assert {q: st[q] for q in ost} == ost and np.array_equal(plans, oplans)
+
+
+# ---- K2 --------------------------------------------------------------------------------------------
+def _check_assign(td, cost, ref_obj=None):
+    cost = np.asarray(cost, dtype=np.int32)
+    n = cost.shape[0]
+    x, col, obj, st = td.solve_full(n, cost)
+    if ref_obj is None:
+        ref_obj = assign_ref.solve_scipy(cost)[0]
+    assert obj == ref_obj, (obj, ref_obj)
+    assert assign_ref.check_x(x, n)                              # row sums = column sums = 1, binary
+    assert sorted(col.tolist()) == list(range(n))
+    assert int(cost[np.arange(n), col].sum()) == obj
+    assert np.array_equal(np.nonzero(x.reshape(n, n))[1], col)  # x[n*cab + cust] layout (procedure.py:56)
+    return st
+
+
+def test_assign_kats(td):
+    gold = load_golden("assign.json")
+    for key in ("A1_python_py", "A2_glpk_mod", "A3_procedure_py"):
+        _check_assign(td, np.array(gold[key]["cost"]), gold[key]["objective"])
+    x = td.solve(4, gold["A1_python_py"]["cost"])
+    perm = np.nonzero(np.asarray(x).reshape(4, 4))[1].tolist()
+    assert perm in gold["A1_python_py"]["optimal_perms"]
+    assert td.solve(0, []) == (0, [])                            # solver.py:12
+
+
+def test_assign_config1(td):
+    gold = load_golden("assign.json")
+    _check_assign(td, g.config1a(), gold["config1a"]["objective"])
+    # LP-relaxation clause of north_star: |objective - LP optimum of the reference model| <= 1e-9 relative
+    assert abs(gold["config1a"]["lp"] - gold["config1a"]["objective"]) <= 1e-9 * gold["config1a"]["objective"]
+    dist, cab_to, cust_from = g.config1b()
+    n, cost = cost_ref.calculate_cost_np(dist, cab_to, cust_from)
+    _check_assign(td, cost, gold["config1b"]["objective"])
+    assert abs(gold["config1b"]["lp"] - gold["config1b"]["objective"]) <= 1e-9 * gold["config1b"]["objective"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 17, 64, 130, 257, 301])
+def test_assign_random_small(td, n):
+    rng = np.random.default_rng(100 + n)
+    _check_assign(td, rng.integers(1, 40, (n, n)))
+    _check_assign(td, rng.integers(0, 3, (n, n)))               # brutal ties
+    _check_assign(td, rng.integers(0, 250001, (n, n)))          # wide range
+    _check_assign(td, np.full((n, n), 7))                        # all equal
+    _check_assign(td, rng.integers(-50, 50, (n, n)))            # negative costs
+
+
+def test_assign_structured(td):
+    rng = np.random.default_rng(77)
+    for n_cabs, n_cust, S, cutoff in ((120, 200, 50, None), (200, 120, 50, 10), (218, 600, 50, 10), (600, 351, 50, 10)):
+        dist = g.stand_distances(S)
+        n, cost = cost_ref.calculate_cost_np(dist, rng.integers(0, S, n_cabs), rng.integers(0, S, n_cust), cutoff=cutoff)
+        _check_assign(td, cost)
+    _check_assign(td, np.abs(np.arange(150)[:, None] - np.arange(150)[None, :]))   # identity optimum, objective 0
+    _check_assign(td, (np.arange(90)[:, None] * np.arange(90)[None, :]) % 17)
+
+
+def test_assign_config2_and_mid_sizes(td):
+    gold = load_golden("assign.json")
+    _check_assign(td, g.config2(), gold["config2"]["objective"])
+    _check_assign(td, g.config2_stand(), gold["config2_stand"]["objective"])
+    _check_assign(td, g.config5a(5000), gold["config5a_n5000"]["objective"])
+    _check_assign(td, g.config5b_cost(5000), gold["config5b_n5000"]["objective"])
+
+
+def test_assign_optimum_not_above_lcm(td):
+    """heuristic.py:40's invariant: the optimum never exceeds the LCM total"""
+    C = g.config2()[:400, :400].copy()
+    _, _, obj, _ = td.solve_full(400, C)
+    assert obj <= td.LCM_heuristic(400, C)
