@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Small, deterministic driver for ncu captures: one invocation of each hot-path kernel on its
+BASELINE.json shape.  Usage (on the GPU box, see profiles/README.md):
+    python profiles/prof_driver.py [pool] [cost] [lcm] [assign5a] [assign2s]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import taxidispatcher_b200 as td  # noqa: E402
+from oracle import gen_inputs as g  # noqa: E402
+
+which = sys.argv[1:] or ["pool", "cost", "lcm", "assign5a"]
+eng = td.engine()
+if "pool" in which:
+    dem = torch.from_numpy(g.pool_demand()).cuda()
+    dist = torch.from_numpy(g.stand_distances(50)).cuda()
+    for sh in (0, 1):
+        out, cnt, st = eng.pool_find(dem, dist, 4, sh, 8)
+        print("pool shard", sh, st.evaluated, st.feasible, st.kept, st.rounds)
+if "cost" in which:
+    cab_to, cust_from = g.config5b()
+    d = torch.from_numpy(g.stand_distances(4000)).cuda()
+    out = None
+    for _ in range(3):
+        out = eng.cost_matrix(d, torch.from_numpy(cab_to).cuda(), torch.from_numpy(cust_from).cuda(), out=out)
+    torch.cuda.synchronize()
+    print("cost", int(out[123, 456]))
+if "lcm" in which:
+    c = torch.from_numpy(g.config2()).cuda()
+    for _ in range(2):
+        r = eng.lcm_host_view(*eng.lcm(c, 100))
+    print("lcm", r["total"])
+if "assign5a" in which:
+    c = torch.from_numpy(g.config5a()).cuda()
+    col, obj, _, st = eng.assign(c, want_stats=True)
+    print("assign5a", int(obj.item()), st.phases, st.search_steps, st.rows_scanned)
+if "assign2s" in which:
+    c = torch.from_numpy(g.config2_stand()).cuda()
+    col, obj, _, st = eng.assign(c, want_stats=True)
+    print("assign2s", int(obj.item()), st.phases, st.search_steps, st.rows_scanned)
+torch.cuda.synchronize()
