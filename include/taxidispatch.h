@@ -160,6 +160,19 @@ int td_pool_find(const int32_t *demand, int n, const int32_t *dist, int n_stands
                  td_pool_stats *stats /* host, may be NULL */,
                  void *workspace, size_t workspace_bytes, int64_t max_feasible, void *stream);
 
+/* Several CONSECUTIVE logical shards [shard_begin, shard_begin + shard_count) in one call (shard_count <= 64):
+ * one enumeration launch and one selection launch serve all of them (the shards stay independent --
+ * each keeps its own dedup state, exactly like separate pool_n processes).  plans_out holds
+ * shard_count blocks of `cap` rows, counts_out[s] the survivors of shard shard_begin + s (-1 if the
+ * record list overflowed); stats is a HOST array of shard_count entries (may be NULL). */
+size_t td_pool_shards_workspace_bytes(int n, int n_stands, int pool_size, int shard_count, int64_t max_feasible);
+int td_pool_find_shards(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
+                        int shard_begin, int shard_count, int n_shards,
+                        int32_t *plans_out /* shard_count x cap x 9 */, int32_t cap, int32_t *counts_out /* shard_count */,
+                        td_pool_stats *stats /* host[shard_count], may be NULL */,
+                        void *workspace, size_t workspace_bytes, int64_t max_feasible /* all shards together */,
+                        void *stream);
+
 /* findpool.c:83-108: concatenated shard survivors (shard order) -> sort on column 8 -> greedy
  * disjoint scan.  Reference quirk kept: for pool_size < 4 findpool.c sorts on a column it never
  * filled (findpool.c:34-35,70), so the scan runs in concatenation order. */

@@ -229,32 +229,41 @@ extern "C" int tdh_pool_find(const int32_t *demand, int n, const int32_t *dist, 
 
 extern "C" int tdh_pool_find_all(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
                                  int n_shards, int32_t *plans_out, int32_t cap, int32_t *n_plans_out, td_pool_stats *stats) {
-    if (n < 0 || n_stands <= 0 || n_shards < 1 || !n_plans_out || cap < 0) return TD_ERR_INVALID;
+    if (n < 0 || n_stands <= 0 || n_shards < 1 || n_shards > 64 || !n_plans_out || cap < 0) return TD_ERR_INVALID;
     if (!td::have_device()) return TD_ERR_NO_DEVICE;
     const int per_shard_cap = n / 2 + 1;  // survivors are customer-disjoint: at most n / pool_size per shard
-    td::DevBuf d_dem, d_dist, d_all, d_cnt, d_out, d_ws;
+    td::DevBuf d_dem, d_dist, d_all, d_cnt, d_tot, d_out, d_ws;
     TDH_TRY(d_dem.alloc(size_t(n) * 5 * 4)); TDH_TRY(d_dist.alloc(size_t(n_stands) * n_stands * 4));
-    TDH_TRY(d_all.alloc(size_t(per_shard_cap) * n_shards * TD_POOL_REC_W * 4)); TDH_TRY(d_cnt.alloc(4));
+    TDH_TRY(d_all.alloc(size_t(per_shard_cap) * n_shards * TD_POOL_REC_W * 4)); TDH_TRY(d_cnt.alloc(size_t(n_shards) * 4));
+    TDH_TRY(d_tot.alloc(4));
     if (n) TDH_TRY(cudaMemcpy(d_dem.p, demand, size_t(n) * 5 * 4, cudaMemcpyHostToDevice));
     TDH_TRY(cudaMemcpy(d_dist.p, dist, size_t(n_stands) * n_stands * 4, cudaMemcpyHostToDevice));
+    std::vector<td_pool_stats> st(n_shards);
+    int64_t max_feasible = int64_t(1) << 22;
+    int rc = TD_ERR_CAPACITY;
+    for (int attempt = 0; attempt < 8 && rc == TD_ERR_CAPACITY; ++attempt) {
+        td::DevBuf ws;
+        const size_t wsb = td_pool_shards_workspace_bytes(n, n_stands, pool_size, n_shards, max_feasible);
+        TDH_TRY(ws.alloc(wsb));
+        rc = td_pool_find_shards(d_dem.as<int32_t>(), n, d_dist.as<int32_t>(), n_stands, pool_size, 0, n_shards, n_shards,
+                                 d_all.as<int32_t>(), per_shard_cap, d_cnt.as<int32_t>(), st.data(), ws.p, wsb, max_feasible, nullptr);
+        int64_t need = 0;
+        for (auto &q : st) need += q.feasible;
+        if (rc == TD_ERR_CAPACITY && need <= max_feasible) break;
+        max_feasible = need + 1024;
+    }
+    if (rc != TD_OK) return rc;
     td_pool_stats tot;
     memset(&tot, 0, sizeof tot);
-    int total = 0;
-    for (int sh = 0; sh < n_shards; ++sh) {
-        td_pool_stats st;
-        int32_t *dst = d_all.as<int32_t>() + size_t(total) * TD_POOL_REC_W;
-        TDH_RC(pool_find_retry(d_dem.as<int32_t>(), n, d_dist.as<int32_t>(), n_stands, pool_size, sh, n_shards, dst,
-                               per_shard_cap, d_cnt.as<int32_t>(), &st));
-        int32_t c = 0;
-        TDH_TRY(cudaMemcpy(&c, d_cnt.p, 4, cudaMemcpyDeviceToHost));
-        total += c;
-        tot.evaluated += st.evaluated; tot.feasible += st.feasible; tot.rounds += st.rounds; tot.passes += st.passes;
-    }
+    for (auto &q : st) { tot.evaluated += q.evaluated; tot.feasible += q.feasible; }
+    tot.rounds = st[0].rounds; tot.passes = 1;
+    const int total = per_shard_cap * n_shards;
     TDH_TRY(d_out.alloc(size_t(total) * TD_POOL_REC_W * 4));
     const size_t wsb = td_pool_merge_workspace_bytes(total, n);
     TDH_TRY(d_ws.alloc(wsb));
-    TDH_RC(td_pool_merge(d_all.as<int32_t>(), total, n, pool_size, d_out.as<int32_t>(), d_cnt.as<int32_t>(), d_ws.p, wsb, nullptr));
-    TDH_TRY(cudaMemcpy(n_plans_out, d_cnt.p, 4, cudaMemcpyDeviceToHost));
+    TDH_RC(td_pool_merge_padded(d_all.as<int32_t>(), d_cnt.as<int32_t>(), nullptr, n_shards, per_shard_cap, n, pool_size,
+                                d_out.as<int32_t>(), d_tot.as<int32_t>(), d_ws.p, wsb, nullptr));
+    TDH_TRY(cudaMemcpy(n_plans_out, d_tot.p, 4, cudaMemcpyDeviceToHost));
     tot.kept = *n_plans_out;
     if (stats) *stats = tot;
     int m = *n_plans_out < cap ? *n_plans_out : cap;

@@ -5,10 +5,12 @@
 // procedure.py:6-12).  cost[i][j] = dist[cab_to[i]][cust_from[j]], square-padded with `fill`.
 //
 // HBM-write-bound: 4*n^2 bytes out, 4*(n_cabs+n_cust) + 4*S^2 bytes in.  Layout decisions:
-//   * one CTA works on one cab row at a time (persistent grid = multiple of the SM count); the
-//     stand row dist[cab_to[i]][:] is staged in shared memory once per row, so the per-cell
-//     gather hits 32 banks instead of L1 lines;
-//   * cust_from[] is staged in shared memory once per CTA (n_cust * 4 B);
+//   * persistent grid (a multiple of the SM count); one CTA works on one cab row at a time;
+//   * the stand row dist[cab_to[i]][:] is staged in shared memory so the per-cell gather hits 32
+//     banks instead of L1 lines; the NEXT row's stand row is prefetched with cp.async into the
+//     other half of a double buffer while the current row is being written (one __syncthreads per
+//     row, load latency hidden);
+//   * cust_from[] is read with 16-byte read-only loads (80 KB at n = 20k: L1-resident);
 //   * each thread emits 4 consecutive customers as one 16-byte streaming store (st.global.cs);
 //     rows whose start is not 16-byte aligned (n % 4 != 0) get a scalar head/tail;
 //   * cutoff and padding are fused into the same pass.
@@ -16,40 +18,56 @@
 
 namespace td {
 
-constexpr int kCostThreads = 512;
+constexpr int kCostThreads = 256;
+
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <bool kRowInSmem>
 __global__ void __launch_bounds__(kCostThreads)
 cost_matrix_kernel(const int32_t *__restrict__ dist, int n_stands,
                    const int32_t *__restrict__ cab_to, int n_cabs,
                    const int32_t *__restrict__ cust_from, int n_cust,
-                   int32_t fill, int32_t cutoff, int32_t *__restrict__ cost, int n, int cust_in_smem) {
-    extern __shared__ int32_t smem[];
-    int32_t *s_row = smem;                                   // n_stands (only if kRowInSmem)
-    int32_t *s_cust = smem + (kRowInSmem ? n_stands : 0);    // n_cust   (only if cust_in_smem)
+                   int32_t fill, int32_t cutoff, int32_t *__restrict__ cost, int n, int row_stride) {
+    extern __shared__ __align__(16) int32_t smem[];  // [2][row_stride] when kRowInSmem
     const int tid = threadIdx.x;
-    if (cust_in_smem)
-        for (int j = tid; j < n_cust; j += kCostThreads) s_cust[j] = cust_from[j];
-    const int32_t *custp = cust_in_smem ? s_cust : cust_from;
     const bool has_cut = cutoff >= 0;
+    const bool vec_row = (n_stands & 3) == 0 && ((reinterpret_cast<uintptr_t>(dist) & 15) == 0);
+    const bool vec_cust = (reinterpret_cast<uintptr_t>(cust_from) & 15) == 0;
 
-    for (int row = blockIdx.x; row < n; row += gridDim.x) {
+    auto prefetch = [&](int row, int buf) {
+        if (!kRowInSmem || row >= n_cabs) return;
+        const int32_t *src = dist + size_t(cab_to[row]) * n_stands;
+        int32_t *dst = smem + buf * row_stride;
+        if (vec_row) for (int s = tid * 4; s < n_stands; s += kCostThreads * 4) cp_async_16(dst + s, src + s);
+        else for (int s = tid; s < n_stands; s += kCostThreads) cp_async_4(dst + s, src + s);
+    };
+
+    int row = blockIdx.x;
+    prefetch(row, 0);
+    for (int it = 0; row < n; row += gridDim.x, ++it) {
+        const int cur = it & 1;
+        cp_async_wait_all();
+        __syncthreads();                       // current stand row landed; previous row's readers are done
+        prefetch(row + gridDim.x, cur ^ 1);    // overlaps with the stores below
         int32_t *out = cost + size_t(row) * n;
         const bool real_row = row < n_cabs;
-        const int32_t *drow = nullptr;
-        __syncthreads();  // previous row's readers are done with s_row; also orders the s_cust fill
-        if (real_row) {
-            drow = dist + size_t(cab_to[row]) * n_stands;
-            if (kRowInSmem) {
-                for (int s = tid; s < n_stands; s += kCostThreads) s_row[s] = drow[s];
-                __syncthreads();
-                drow = s_row;
-            }
-        }
+        const int32_t *drow = !real_row ? nullptr
+                              : (kRowInSmem ? smem + cur * row_stride : dist + size_t(cab_to[row]) * n_stands);
+        auto lookup = [&](int stand) -> int32_t {
+            const int32_t d = kRowInSmem ? drow[stand] : __ldg(drow + stand);
+            return (has_cut && d >= cutoff) ? fill : d;
+        };
         auto cell = [&](int j) -> int32_t {
             if (!real_row || j >= n_cust) return fill;
-            int32_t d = drow[custp[j]];
-            return (has_cut && d >= cutoff) ? fill : d;
+            return lookup(__ldg(cust_from + j));
         };
         // scalar head up to the first 16-byte aligned element of this row
         const int head = int((4 - ((size_t(row) * n) & 3)) & 3);
@@ -57,15 +75,34 @@ cost_matrix_kernel(const int32_t *__restrict__ dist, int n_stands,
         if (tid < h) out[tid] = cell(tid);
         const int nvec = (n - h) >> 2;
         int4 *outv = reinterpret_cast<int4 *>(out + h);
-        for (int v = tid; v < nvec; v += kCostThreads) {
-            const int j = h + (v << 2);
-            int4 r;
-            r.x = cell(j); r.y = cell(j + 1); r.z = cell(j + 2); r.w = cell(j + 3);
-            __stcs(outv + v, r);
+        if (!real_row) {
+            const int4 f = make_int4(fill, fill, fill, fill);
+            for (int v = tid; v < nvec; v += kCostThreads) __stcs(outv + v, f);
+        } else if (h == 0 && vec_cust) {
+#pragma unroll 2
+            for (int v = tid; v < nvec; v += kCostThreads) {
+                const int j = v << 2;
+                int4 r;
+                if (j + 3 < n_cust) {
+                    const int4 cf = __ldg(reinterpret_cast<const int4 *>(cust_from + j));
+                    r.x = lookup(cf.x); r.y = lookup(cf.y); r.z = lookup(cf.z); r.w = lookup(cf.w);
+                } else {
+                    r.x = cell(j); r.y = cell(j + 1); r.z = cell(j + 2); r.w = cell(j + 3);
+                }
+                __stcs(outv + v, r);
+            }
+        } else {
+            for (int v = tid; v < nvec; v += kCostThreads) {
+                const int j = h + (v << 2);
+                int4 r;
+                r.x = cell(j); r.y = cell(j + 1); r.z = cell(j + 2); r.w = cell(j + 3);
+                __stcs(outv + v, r);
+            }
         }
         const int tail0 = h + (nvec << 2);
-        if (tail0 + tid < n && tid < 4) out[tail0 + tid] = cell(tail0 + tid);
+        if (tid < 4 && tail0 + tid < n) out[tail0 + tid] = cell(tail0 + tid);
     }
+    cp_async_wait_all();
 }
 
 }  // namespace td
@@ -79,27 +116,23 @@ extern "C" int td_cost_matrix(const int32_t *dist, int n_stands, const int32_t *
     if (!cost_out || (n_cabs > 0 && n_cust > 0 && (!dist || !cab_to || !cust_from || n_stands == 0))) return TD_ERR_INVALID;
     if (!td::have_device()) return TD_ERR_NO_DEVICE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t kSmemBudget = 200 * 1024;
-    const bool row_in_smem = size_t(n_stands) * 4 <= 96 * 1024;
-    size_t smem = row_in_smem ? size_t(n_stands) * 4 : 0;
-    const int cust_in_smem = (smem + size_t(n_cust) * 4 <= kSmemBudget) ? 1 : 0;
-    if (cust_in_smem) smem += size_t(n_cust) * 4;
+    const int row_stride = (n_stands + 3) & ~3;
+    const bool row_in_smem = size_t(row_stride) * 8 <= 96 * 1024;   // two buffers
+    const size_t smem = row_in_smem ? size_t(row_stride) * 8 : 0;
     const int sms = td::device_sm_count();
-    // enough CTAs per SM to hide the per-row staging latency; never more CTAs than rows
-    const size_t per_cta = smem > 1024 ? smem : 1024;
-    int per_sm = int((220 * 1024) / per_cta);
-    per_sm = per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm);
+    int per_sm = 8;
+    if (smem > 0) { const int fit = int((200 * 1024) / smem); per_sm = fit < per_sm ? fit : per_sm; }
+    per_sm = per_sm < 1 ? 1 : per_sm;
     int grid = sms * per_sm;
     if (grid > n) grid = n;
     td::ProfScope prof(TD_PROF_COST, st);
     if (row_in_smem) {
-        TD_CUDA_TRY(cudaFuncSetAttribute(td::cost_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
+        TD_CUDA_TRY(cudaFuncSetAttribute(td::cost_matrix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(96 * 1024)));
         td::cost_matrix_kernel<true><<<grid, td::kCostThreads, smem, st>>>(dist, n_stands, cab_to, n_cabs, cust_from, n_cust,
-                                                                           fill, cutoff, cost_out, n, cust_in_smem);
+                                                                           fill, cutoff, cost_out, n, row_stride);
     } else {
-        TD_CUDA_TRY(cudaFuncSetAttribute(td::cost_matrix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBudget)));
-        td::cost_matrix_kernel<false><<<grid, td::kCostThreads, smem, st>>>(dist, n_stands, cab_to, n_cabs, cust_from, n_cust,
-                                                                            fill, cutoff, cost_out, n, cust_in_smem);
+        td::cost_matrix_kernel<false><<<grid, td::kCostThreads, 0, st>>>(dist, n_stands, cab_to, n_cabs, cust_from, n_cust,
+                                                                         fill, cutoff, cost_out, n, row_stride);
     }
     TD_LAUNCH_CHECK();
     return TD_OK;

@@ -60,16 +60,17 @@ struct PoolRec {                  // 16 bytes
     int32_t pad;
 };
 
+constexpr int kMaxSlots = 64;     // logical shards handled by one call
+
 struct PoolCtrl {
-    unsigned long long evaluated, feasible;
+    unsigned long long evaluated[kMaxSlots], feasible[kMaxSlots];  // per logical shard of this call
+    unsigned int n_kept[kMaxSlots];
     unsigned int n_records;       // slots reserved in the record list
     unsigned int item_counter;
     unsigned int overflow;
     unsigned int n_items;
-    unsigned int n_kept;
     unsigned int rounds;
     unsigned int list_count[2];   // live records in the ping-pong lists of pool_select
-    int32_t max_wait;
 };
 
 __device__ __forceinline__ unsigned long long make_rank(int p0, int p1, int p2, int p3, int perm) {
@@ -139,17 +140,31 @@ pool_build_lists_kernel(const int4 *__restrict__ cust, int n, const int32_t *__r
 }
 
 // items per leader (exclusive prefix).  K >= 3: one item per (leader, first-level candidate).
-__global__ void pool_item_offsets_kernel(const int4 *__restrict__ cust, const int32_t *__restrict__ cnt, int start,
-                                         int stop, int pool_size, unsigned int *item_off, PoolCtrl *ctrl) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;  // <= n/n_shards+1 leaders: a serial scan is fine
-    unsigned run = 0;
-    for (int p0 = start; p0 < stop; ++p0) {
-        item_off[p0 - start] = run;
+__global__ void __launch_bounds__(1024)
+pool_item_offsets_kernel(const int4 *__restrict__ cust, const int32_t *__restrict__ cnt, int start, int stop,
+                         int pool_size, unsigned int *item_off, PoolCtrl *ctrl) {
+    __shared__ unsigned s_part[1024];
+    const int nl = stop - start;
+    const int chunk = (nl + 1023) / 1024;
+    const int lo = min(int(threadIdx.x) * chunk, nl), hi = min(lo + chunk, nl);
+    auto items_of = [&](int p0) -> unsigned {
         const int4 r = cust[p0];
-        if (r.w >= 0) run += pool_size >= 3 ? unsigned(cnt[size_t(r.x) * kTbl + 0]) : 1u;  // pool_n.c:172 at level 0
+        if (r.w < 0) return 0u;                                  // pool_n.c:172 at level 0
+        return pool_size >= 3 ? unsigned(cnt[size_t(r.x) * kTbl + 0]) : 1u;
+    };
+    unsigned sum = 0;
+    for (int t = lo; t < hi; ++t) sum += items_of(start + t);
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int t = 0; t < 1024; ++t) { const unsigned v = s_part[t]; s_part[t] = run; run += v; }
+        item_off[nl] = run;
+        ctrl->n_items = run;
     }
-    item_off[stop - start] = run;
-    ctrl->n_items = run;
+    __syncthreads();
+    unsigned run = s_part[threadIdx.x];
+    for (int t = lo; t < hi; ++t) { item_off[t] = run; run += items_of(start + t); }
 }
 
 // ---- enumeration ---------------------------------------------------------------------------------
@@ -157,6 +172,7 @@ struct EnumArgs {
     const int4 *cust; const int32_t *dist; const int32_t *list; const int32_t *slack; const int32_t *cnt;
     const unsigned int *item_off; PoolRec *recs; PoolCtrl *ctrl;
     int n, S, start, stop; unsigned int cap;
+    int step, shard_begin;        // leader p0 belongs to call slot p0 / step - shard_begin
 };
 
 template <bool kDistSmem>
@@ -275,7 +291,20 @@ pool_enum_kernel(EnumArgs a) {
     const unsigned n_items = a.ctrl->n_items;
     const int n_lead = a.stop - a.start;
     unsigned long long my_eval = 0, my_feas = 0;
+    int cur_slot = -1;
     WarpOut wo{0xffffffffu, unsigned(kChunk)};
+    auto flush_counts = [&]() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
+            my_feas += __shfl_xor_sync(0xffffffffu, my_feas, o);
+        }
+        if (lane == 0 && cur_slot >= 0) {
+            if (my_eval) atomicAdd(&a.ctrl->evaluated[cur_slot], my_eval);
+            if (my_feas) atomicAdd(&a.ctrl->feasible[cur_slot], my_feas);
+        }
+        my_eval = 0; my_feas = 0;
+    };
 
     for (;;) {
         unsigned item = 0;
@@ -290,6 +319,8 @@ pool_enum_kernel(EnumArgs a) {
         }
         const int p0 = a.start + lo;
         const int4 c0 = cust[p0];
+        const int slot = p0 / a.step - a.shard_begin;
+        if (slot != cur_slot) { flush_counts(); cur_slot = slot; }
 
         if (K == 2) {
             // lanes over p1
@@ -397,15 +428,7 @@ pool_enum_kernel(EnumArgs a) {
     // close the last chunk, publish the counters
     if (wo.base != 0xffffffffu)
         for (unsigned t = wo.used + lane; t < kChunk; t += 32) a.recs[wo.base + t].cost = -1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
-        my_feas += __shfl_xor_sync(0xffffffffu, my_feas, o);
-    }
-    if (lane == 0) {
-        if (my_eval) atomicAdd(&a.ctrl->evaluated, my_eval);
-        if (my_feas) atomicAdd(&a.ctrl->feasible, my_feas);
-    }
+    flush_counts();
 }
 
 // ---- selection -----------------------------------------------------------------------------------
@@ -413,6 +436,7 @@ struct SelArgs {
     PoolRec *list[2]; PoolCtrl *ctrl;
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolRec *kept;
     int n, K;
+    int n_slots, step, shard_begin, keep_cap;   // per-slot state lives at [slot * n + customer]
 };
 
 __device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
@@ -426,7 +450,8 @@ pool_select_kernel(SelArgs a) {
     const unsigned nthreads = gridDim.x * blockDim.x;
     const unsigned lane = threadIdx.x & 31;
     const int K = a.K;
-    for (unsigned c = tid; c < unsigned(a.n); c += nthreads) {
+    const unsigned n_state = unsigned(a.n) * unsigned(a.n_slots);
+    for (unsigned c = tid; c < n_state; c += nthreads) {
         a.alive[c] = 1;
         a.best_hi[0][c] = a.best_hi[1][c] = ~0ull;
         a.best_lo[0][c] = a.best_lo[1][c] = ~0u;
@@ -451,7 +476,8 @@ pool_select_kernel(SelArgs a) {
                 if (r.cost >= 0) {
                     split_rank(r.rank, p, perm);
                     live = true;
-                    for (int q = 0; q < K; ++q) live = live && a.alive[p[q]];
+                    const int so = (p[0] / a.step - a.shard_begin) * a.n;
+                    for (int q = 0; q < K; ++q) { p[q] += so; live = live && a.alive[p[q]]; }
                 }
             }
             const unsigned ball = __ballot_sync(0xffffffffu, live);
@@ -472,10 +498,11 @@ pool_select_kernel(SelArgs a) {
             const PoolRec r = dst[i];
             int p[4], perm;
             split_rank(r.rank, p, perm);
+            const int so = (p[0] / a.step - a.shard_begin) * a.n;
             const unsigned long long hi = rec_hi(r);
             const unsigned lo = unsigned(r.rank);
             for (int q = 0; q < K; ++q)
-                if (a.best_hi[b][p[q]] == hi && lo < a.best_lo[b][p[q]]) atomicMin(&a.best_lo[b][p[q]], lo);
+                if (a.best_hi[b][so + p[q]] == hi && lo < a.best_lo[b][so + p[q]]) atomicMin(&a.best_lo[b][so + p[q]], lo);
         }
         if (tid == 0) a.ctrl->list_count[cur] = 0;  // becomes the destination of the next round
         grid.sync();
@@ -484,18 +511,20 @@ pool_select_kernel(SelArgs a) {
             const PoolRec r = dst[i];
             int p[4], perm;
             split_rank(r.rank, p, perm);
+            const int slot = p[0] / a.step - a.shard_begin;
+            const int so = slot * a.n;
             const unsigned long long hi = rec_hi(r);
             const unsigned lo = unsigned(r.rank);
             bool dom = true;
-            for (int q = 0; q < K; ++q) dom = dom && a.best_hi[b][p[q]] == hi && a.best_lo[b][p[q]] == lo;
+            for (int q = 0; q < K; ++q) dom = dom && a.best_hi[b][so + p[q]] == hi && a.best_lo[b][so + p[q]] == lo;
             if (dom) {
-                const unsigned slot = atomicAdd(&a.ctrl->n_kept, 1u);
-                a.kept[slot] = r;
-                for (int q = 0; q < K; ++q) a.alive[p[q]] = 0;
+                const unsigned pos = atomicAdd(&a.ctrl->n_kept[slot], 1u);
+                a.kept[size_t(slot) * a.keep_cap + pos] = r;
+                for (int q = 0; q < K; ++q) a.alive[so + p[q]] = 0;
             }
         }
         // reset the other parity's minima for the next round (nobody reads them in this round)
-        for (unsigned c = tid; c < unsigned(a.n); c += nthreads) { a.best_hi[b ^ 1][c] = ~0ull; a.best_lo[b ^ 1][c] = ~0u; }
+        for (unsigned c = tid; c < n_state; c += nthreads) { a.best_hi[b ^ 1][c] = ~0ull; a.best_lo[b ^ 1][c] = ~0u; }
         grid.sync();
         cur ^= 1;
     }
@@ -503,9 +532,13 @@ pool_select_kernel(SelArgs a) {
 
 // kept plans -> ascending (cost, rank) -> pool_n.c:123-134 records
 __global__ void __launch_bounds__(1024)
-pool_emit_kernel(const PoolRec *__restrict__ kept, const PoolCtrl *ctrl, int K, int32_t *plans_out, int32_t cap,
-                 int32_t *n_plans_out) {
-    const int m = int(ctrl->n_kept);
+pool_emit_kernel(const PoolRec *__restrict__ kept_all, const PoolCtrl *ctrl, int K, int keep_cap, int32_t *plans_all,
+                 int32_t cap, int32_t *counts_out) {
+    const int slot = blockIdx.x;
+    const PoolRec *kept = kept_all + size_t(slot) * keep_cap;
+    int32_t *plans_out = plans_all + size_t(slot) * cap * TD_POOL_REC_W;
+    int32_t *n_plans_out = counts_out + slot;
+    const int m = int(ctrl->n_kept[slot]);
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         const PoolRec me = kept[i];
         int rank = 0;
@@ -542,83 +575,107 @@ pool_emit_kernel(const PoolRec *__restrict__ kept, const PoolCtrl *ctrl, int K, 
 }
 
 // ---- merge (findpool.c:83-108) ---------------------------------------------------------------
-// total <= n_shards * (n/2+1) rows; runs in one CTA: stable order by column 8 (or concatenation
-// order for K < 4, see header), then the same dominance rounds on the tiny list.
-// Padded form: `counts` != NULL -> row i belongs to slot i / cap and is valid iff i % cap < counts[slot];
-// slot_shard[slot] gives the logical shard of the slot (concatenation order = shard order).
+// One CTA.  Valid rows are compacted first (padded layout: row i belongs to slot i / cap and is
+// valid iff i % cap < counts[slot]; slot_shard[slot] = logical shard, concatenation order = shard
+// order).  Scan order = (column 8, concatenation position) for K == 4, concatenation position
+// otherwise (see header: findpool.c sorts on a column it never filled for K < 4).  Then the same
+// dominance rounds as pool_select on the small list.
 __global__ void __launch_bounds__(1024)
 pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, const int32_t *__restrict__ counts, int cap,
-                  const int32_t *__restrict__ slot_shard, int32_t *order_key /* total */, int32_t *owner /* n */,
-                  uint8_t *state /* total: 0 live, 1 kept, 2 dead */, int32_t *plans_out, int32_t *n_plans_out) {
-    __shared__ int s_live;
+                  const int32_t *__restrict__ slot_shard, unsigned long long *ckey /* total */, int32_t *crow /* total */,
+                  int32_t *order_key /* total */, int32_t *owner /* n */, uint8_t *state /* total */,
+                  int32_t *plans_out, int32_t *n_plans_out) {
+    __shared__ int s_m, s_live;
+    __shared__ unsigned long long tile[1024];
     const int tid = threadIdx.x;
-    auto valid = [&](int i) -> bool { return !counts || (i % cap) < counts[i / cap]; };
-    auto concat_pos = [&](int i) -> long long {
-        if (!counts) return i;
-        const int slot = i / cap;
-        return (long long)(slot_shard ? slot_shard[slot] : slot) * cap + (i % cap);
-    };
-    // position of every row in the scan order: (cost, concatenation index) for K == 4, index otherwise
-    for (int i = tid; i < total; i += blockDim.x) {
-        if (!valid(i)) { state[i] = 2; order_key[i] = INT_MAX; continue; }
-        const int ci = K == TD_POOL_MAX_IN_POOL ? plans[size_t(i) * TD_POOL_REC_W + 8] : 0;
-        const long long pi = concat_pos(i);
-        int pos = 0;
-        for (int j = 0; j < total; ++j) {
-            if (!valid(j)) continue;
-            const int cj = K == TD_POOL_MAX_IN_POOL ? plans[size_t(j) * TD_POOL_REC_W + 8] : 0;
-            pos += (cj < ci) || (cj == ci && concat_pos(j) < pi);
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += blockDim.x) {
+        const int i = base + tid;
+        bool ok = false;
+        long long pos = 0;
+        if (i < total) {
+            if (counts) {
+                const int slot = i / cap, r = i % cap;
+                ok = r < counts[slot];
+                pos = (long long)(slot_shard ? slot_shard[slot] : slot) * cap + r;
+            } else {
+                ok = true; pos = i;
+            }
         }
-        order_key[i] = pos;
-        state[i] = 0;
+        if (ok) {
+            const int c = atomicAdd(&s_m, 1);
+            const unsigned long long costpart = K == TD_POOL_MAX_IN_POOL ? (unsigned long long)(unsigned)plans[size_t(i) * TD_POOL_REC_W + 8] : 0ull;
+            ckey[c] = (costpart << 32) | (unsigned long long)pos;   // pos < 2^32 (total <= 2^24 rows)
+            crow[c] = i;
+        }
+    }
+    __syncthreads();
+    const int m = s_m;
+    // rank = number of smaller keys (keys are unique)
+    for (int base = 0; base < m; base += blockDim.x) {
+        const int me = base + tid;
+        const unsigned long long mine = me < m ? ckey[me] : ~0ull;
+        int rank = 0;
+        for (int t0 = 0; t0 < m; t0 += 1024) {
+            __syncthreads();
+            tile[tid] = (t0 + tid < m) ? ckey[t0 + tid] : ~0ull;
+            __syncthreads();
+            const int lim = (m - t0) < 1024 ? (m - t0) : 1024;
+            for (int t = 0; t < lim; ++t) rank += tile[t] < mine;
+        }
+        if (me < m) { order_key[me] = rank; state[me] = 0; }
     }
     __syncthreads();
     for (;;) {
         for (int c = tid; c < n; c += blockDim.x) owner[c] = INT_MAX;
         if (tid == 0) s_live = 0;
         __syncthreads();
-        for (int i = tid; i < total; i += blockDim.x)
+        for (int i = tid; i < m; i += blockDim.x)
             if (state[i] == 0) {
                 s_live = 1;
-                for (int q = 0; q < K; ++q) atomicMin(&owner[plans[size_t(i) * TD_POOL_REC_W + q]], order_key[i]);
+                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+                for (int q = 0; q < K; ++q) atomicMin(&owner[row[q]], order_key[i]);
             }
         __syncthreads();
         if (!s_live) break;
-        for (int i = tid; i < total; i += blockDim.x)
+        for (int i = tid; i < m; i += blockDim.x)
             if (state[i] == 0) {
+                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
                 bool dom = true;
-                for (int q = 0; q < K; ++q) dom = dom && owner[plans[size_t(i) * TD_POOL_REC_W + q]] == order_key[i];
+                for (int q = 0; q < K; ++q) dom = dom && owner[row[q]] == order_key[i];
                 if (dom) state[i] = 1;
             }
         __syncthreads();
-        // mark customers of kept plans, then kill the live plans touching them
-        for (int c = tid; c < n; c += blockDim.x) owner[c] = 0;
+        // customers of kept plans are taken: every other live plan touching them dies
+        for (int i = tid; i < m; i += blockDim.x)
+            if (state[i] == 1) {
+                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+                for (int q = 0; q < K; ++q) owner[row[q]] = -1;
+            }
         __syncthreads();
-        for (int i = tid; i < total; i += blockDim.x)
-            if (state[i] == 1)
-                for (int q = 0; q < K; ++q) owner[plans[size_t(i) * TD_POOL_REC_W + q]] = 1;
-        __syncthreads();
-        for (int i = tid; i < total; i += blockDim.x)
+        for (int i = tid; i < m; i += blockDim.x)
             if (state[i] == 0) {
+                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
                 bool hit = false;
-                for (int q = 0; q < K; ++q) hit = hit || owner[plans[size_t(i) * TD_POOL_REC_W + q]] == 1;
+                for (int q = 0; q < K; ++q) hit = hit || owner[row[q]] == -1;
                 if (hit) state[i] = 2;
             }
         __syncthreads();
     }
-    // output the kept rows in scan order
-    for (int i = tid; i < total; i += blockDim.x)
+    // kept rows in scan order: position = number of kept rows with a smaller scan rank
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    for (int i = tid; i < m; i += blockDim.x)
         if (state[i] == 1) {
             int pos = 0;
-            for (int j = 0; j < total; ++j) pos += (state[j] == 1 && order_key[j] < order_key[i]);
-            for (int t = 0; t < TD_POOL_REC_W; ++t) plans_out[size_t(pos) * TD_POOL_REC_W + t] = plans[size_t(i) * TD_POOL_REC_W + t];
+            for (int j = 0; j < m; ++j) pos += (state[j] == 1 && order_key[j] < order_key[i]);
+            const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+            for (int t = 0; t < TD_POOL_REC_W; ++t) plans_out[size_t(pos) * TD_POOL_REC_W + t] = row[t];
+            atomicAdd(&s_m, 1);
         }
     __syncthreads();
-    if (tid == 0) {
-        int m = 0;
-        for (int i = 0; i < total; ++i) m += state[i] == 1;
-        *n_plans_out = m;
-    }
+    if (tid == 0) *n_plans_out = s_m;
 }
 
 struct PoolWorkspace {
@@ -626,27 +683,31 @@ struct PoolWorkspace {
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolCtrl *ctrl; size_t bytes;
 };
 
-static PoolWorkspace carve_pool(void *ws, int n, int S, int64_t max_feasible) {
+static PoolWorkspace carve_pool(void *ws, int n, int S, int n_slots, int64_t max_records) {
     Carver c(ws);
     PoolWorkspace w;
     const size_t nn = n > 0 ? n : 1;
+    const size_t ns = nn * size_t(n_slots > 0 ? n_slots : 1);
     w.ctrl = c.take<PoolCtrl>(1);
     w.cust = c.take<int4>(nn);
     w.list = c.take<int32_t>(size_t(S) * nn);
     w.slack = c.take<int32_t>(size_t(S) * nn);
     w.cnt = c.take<int32_t>(size_t(S) * kTbl);
     w.item_off = c.take<unsigned int>(nn + 2);
-    w.recs[0] = c.take<PoolRec>(size_t(max_feasible));
-    w.recs[1] = c.take<PoolRec>(size_t(max_feasible));
-    w.kept = c.take<PoolRec>(nn);
-    w.best_hi[0] = c.take<unsigned long long>(nn);
-    w.best_hi[1] = c.take<unsigned long long>(nn);
-    w.best_lo[0] = c.take<unsigned int>(nn);
-    w.best_lo[1] = c.take<unsigned int>(nn);
-    w.alive = c.take<uint8_t>(nn);
+    w.recs[0] = c.take<PoolRec>(size_t(max_records));
+    w.recs[1] = c.take<PoolRec>(size_t(max_records));
+    w.kept = c.take<PoolRec>(size_t(n_slots > 0 ? n_slots : 1) * (nn / 2 + 1));
+    w.best_hi[0] = c.take<unsigned long long>(ns);
+    w.best_hi[1] = c.take<unsigned long long>(ns);
+    w.best_lo[0] = c.take<unsigned int>(ns);
+    w.best_lo[1] = c.take<unsigned int>(ns);
+    w.alive = c.take<uint8_t>(ns);
     w.bytes = c.used();
     return w;
 }
+
+// chunked reservation can strand up to one chunk per resident warp
+static int64_t record_slack() { return int64_t(kChunk) * 148 * 64; }
 
 template <int K>
 static int launch_enum(const EnumArgs &a, int grid, cudaStream_t st) {
@@ -672,51 +733,57 @@ static int launch_enum(const EnumArgs &a, int grid, cudaStream_t st) {
 
 }  // namespace td
 
-extern "C" size_t td_pool_workspace_bytes(int n, int n_stands, int pool_size, int64_t max_feasible) {
+extern "C" size_t td_pool_shards_workspace_bytes(int n, int n_stands, int pool_size, int shard_count, int64_t max_feasible) {
     (void)pool_size;
-    if (n < 0 || n_stands < 0 || max_feasible < 0) return 0;
-    // chunked reservation can strand up to one chunk per resident warp
-    const int64_t slack = int64_t(td::kChunk) * 148 * 64;
-    return td::carve_pool(nullptr, n, n_stands, max_feasible + slack).bytes;
+    if (n < 0 || n_stands < 0 || max_feasible < 0 || shard_count < 1) return 0;
+    return td::carve_pool(nullptr, n, n_stands, shard_count, max_feasible + td::record_slack()).bytes;
 }
 
-extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size, int shard,
-                            int n_shards, int32_t *plans_out, int32_t cap, int32_t *n_plans_out, td_pool_stats *stats,
-                            void *workspace, size_t workspace_bytes, int64_t max_feasible, void *stream) {
+extern "C" size_t td_pool_workspace_bytes(int n, int n_stands, int pool_size, int64_t max_feasible) {
+    return td_pool_shards_workspace_bytes(n, n_stands, pool_size, 1, max_feasible);
+}
+
+extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
+                                   int shard_begin, int shard_count, int n_shards, int32_t *plans_out, int32_t cap,
+                                   int32_t *counts_out, td_pool_stats *stats, void *workspace, size_t workspace_bytes,
+                                   int64_t max_feasible, void *stream) {
     using namespace td;
     if (pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || n < 0 || n > TD_POOL_MAX_CUSTOMERS || n_stands <= 0 ||
-        n_shards < 1 || shard < 0 || shard >= n_shards || cap < 0 || !n_plans_out || max_feasible < 0)
+        n_shards < 1 || shard_begin < 0 || shard_count < 1 || shard_count > kMaxSlots || shard_begin + shard_count > n_shards ||
+        cap < 0 || !counts_out || max_feasible < 0)
         return TD_ERR_INVALID;
     if (n_stands > 32767) return TD_ERR_INVALID;
     if (!have_device()) return TD_ERR_NO_DEVICE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (stats) memset(stats, 0, sizeof *stats);
-    const int step = n / n_shards + 1;                       // pool_n.c:226
-    const int start = step * shard;                          // pool_n.c:227
-    const int stop = start + step > n ? n : start + step;    // pool_n.c:228
+    if (stats) memset(stats, 0, sizeof(*stats) * shard_count);
+    const int step = n / n_shards + 1;                                        // pool_n.c:226
+    const int start = step * shard_begin;                                     // pool_n.c:227
+    const long long stop64 = (long long)step * (shard_begin + shard_count);
+    const int stop = stop64 > n ? n : int(stop64);                            // pool_n.c:228
     if (n == 0 || start >= n) {
-        TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st));
+        TD_CUDA_TRY(cudaMemsetAsync(counts_out, 0, sizeof(int32_t) * shard_count, st));
         if (stats) TD_CUDA_TRY(cudaStreamSynchronize(st));
         return TD_OK;
     }
     if (!demand || !dist || !workspace || (cap > 0 && !plans_out)) return TD_ERR_INVALID;
-    if (workspace_bytes < td_pool_workspace_bytes(n, n_stands, pool_size, max_feasible)) return TD_ERR_WORKSPACE;
-    const int64_t rec_cap64 = max_feasible + int64_t(kChunk) * 148 * 64;
+    if (workspace_bytes < td_pool_shards_workspace_bytes(n, n_stands, pool_size, shard_count, max_feasible)) return TD_ERR_WORKSPACE;
+    const int64_t rec_cap64 = max_feasible + record_slack();
     if (rec_cap64 > 0xfffffff0ll) return TD_ERR_INVALID;
-    PoolWorkspace w = carve_pool(workspace, n, n_stands, rec_cap64);
+    PoolWorkspace w = carve_pool(workspace, n, n_stands, shard_count, rec_cap64);
+    const int keep_cap = n / 2 + 1;
 
     TD_CUDA_TRY(cudaMemsetAsync(w.ctrl, 0, sizeof(PoolCtrl), st));
     pool_prep_cust_kernel<<<(n + 255) / 256, 256, 0, st>>>(demand, n, dist, n_stands, w.cust, w.ctrl);
     TD_LAUNCH_CHECK();
     pool_build_lists_kernel<<<n_stands, 256, 0, st>>>(w.cust, n, dist, n_stands, w.list, w.slack, w.cnt);
     TD_LAUNCH_CHECK();
-    pool_item_offsets_kernel<<<1, 32, 0, st>>>(w.cust, w.cnt, start, stop, pool_size, w.item_off, w.ctrl);
+    pool_item_offsets_kernel<<<1, 1024, 0, st>>>(w.cust, w.cnt, start, stop, pool_size, w.item_off, w.ctrl);
     TD_LAUNCH_CHECK();
 
     EnumArgs ea;
     ea.cust = w.cust; ea.dist = dist; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
     ea.recs = w.recs[0]; ea.ctrl = w.ctrl; ea.n = n; ea.S = n_stands; ea.start = start; ea.stop = stop;
-    ea.cap = unsigned(rec_cap64);
+    ea.cap = unsigned(rec_cap64); ea.step = step; ea.shard_begin = shard_begin;
     const int sms = device_sm_count();
     const int grid = sms * 4;
     int rc;
@@ -730,6 +797,7 @@ extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, i
     sa.list[0] = w.recs[0]; sa.list[1] = w.recs[1]; sa.ctrl = w.ctrl;
     sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
     sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = pool_size;
+    sa.n_slots = shard_count; sa.step = step; sa.shard_begin = shard_begin; sa.keep_cap = keep_cap;
     int per_sm = 0;
     TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_select_kernel, kSelThreads, 0));
     if (per_sm < 1) return TD_ERR_CUDA;
@@ -740,47 +808,65 @@ extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, i
         TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)pool_select_kernel, dim3(sms * per_sm), dim3(kSelThreads), sargs, 0, st));
     }
     count_launch();
-    pool_emit_kernel<<<1, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, plans_out, cap, n_plans_out);
+    pool_emit_kernel<<<shard_count, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, keep_cap, plans_out, cap, counts_out);
     TD_LAUNCH_CHECK();
 
     if (stats) {
-        PoolCtrl h;
+        static thread_local PoolCtrl h;
         TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
         TD_CUDA_TRY(cudaStreamSynchronize(st));
-        stats->evaluated = int64_t(h.evaluated);
-        stats->feasible = int64_t(h.feasible);
-        stats->kept = h.n_kept;
-        stats->rounds = int32_t(h.rounds);
-        stats->passes = 1;
-        if (h.overflow) return TD_ERR_CAPACITY;
-        if (int64_t(h.n_kept) > cap) return TD_ERR_CAPACITY;
+        bool over_cap = false;
+        for (int s = 0; s < shard_count; ++s) {
+            stats[s].evaluated = int64_t(h.evaluated[s]);
+            stats[s].feasible = int64_t(h.feasible[s]);
+            stats[s].kept = h.n_kept[s];
+            stats[s].rounds = int32_t(h.rounds);
+            stats[s].passes = 1;
+            over_cap = over_cap || int64_t(h.n_kept[s]) > cap;
+        }
+        if (h.overflow || over_cap) return TD_ERR_CAPACITY;
     }
     return TD_OK;
 }
 
-extern "C" size_t td_pool_merge_workspace_bytes(int total_plans, int n) {
-    td::Carver c(nullptr);
-    c.take<int32_t>(total_plans > 0 ? total_plans : 1);
-    c.take<int32_t>(n > 0 ? n : 1);
-    c.take<uint8_t>(total_plans > 0 ? total_plans : 1);
-    return c.used();
+extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size, int shard,
+                            int n_shards, int32_t *plans_out, int32_t cap, int32_t *n_plans_out, td_pool_stats *stats,
+                            void *workspace, size_t workspace_bytes, int64_t max_feasible, void *stream) {
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return TD_ERR_INVALID;
+    return td_pool_find_shards(demand, n, dist, n_stands, pool_size, shard, 1, n_shards, plans_out, cap, n_plans_out, stats,
+                               workspace, workspace_bytes, max_feasible, stream);
 }
+
+namespace td {
+struct MergeWs { unsigned long long *ckey; int32_t *crow, *order_key, *owner; uint8_t *state; size_t bytes; };
+static MergeWs carve_merge(void *ws, int total, int n) {
+    Carver c(ws);
+    MergeWs w;
+    const size_t t = total > 0 ? total : 1;
+    w.ckey = c.take<unsigned long long>(t);
+    w.crow = c.take<int32_t>(t);
+    w.order_key = c.take<int32_t>(t);
+    w.owner = c.take<int32_t>(n > 0 ? n : 1);
+    w.state = c.take<uint8_t>(t);
+    w.bytes = c.used();
+    return w;
+}
+}  // namespace td
+
+extern "C" size_t td_pool_merge_workspace_bytes(int total_plans, int n) { return td::carve_merge(nullptr, total_plans, n).bytes; }
 
 extern "C" int td_pool_merge(const int32_t *shard_plans, int total_plans, int n, int pool_size, int32_t *plans_out,
                              int32_t *n_plans_out, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace td;
-    if (total_plans < 0 || n < 0 || pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || !n_plans_out) return TD_ERR_INVALID;
+    if (total_plans < 0 || total_plans > (1 << 24) || n < 0 || pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || !n_plans_out) return TD_ERR_INVALID;
     if (!have_device()) return TD_ERR_NO_DEVICE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (total_plans == 0) { TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st)); return TD_OK; }
     if (!shard_plans || !plans_out || !workspace) return TD_ERR_INVALID;
     if (workspace_bytes < td_pool_merge_workspace_bytes(total_plans, n)) return TD_ERR_WORKSPACE;
-    Carver c(workspace);
-    int32_t *order_key = c.take<int32_t>(total_plans);
-    int32_t *owner = c.take<int32_t>(n > 0 ? n : 1);
-    uint8_t *state = c.take<uint8_t>(total_plans);
-    pool_merge_kernel<<<1, 1024, 0, st>>>(shard_plans, total_plans, n, pool_size, nullptr, 1, nullptr, order_key, owner, state,
-                                          plans_out, n_plans_out);
+    MergeWs w = carve_merge(workspace, total_plans, n);
+    pool_merge_kernel<<<1, 1024, 0, st>>>(shard_plans, total_plans, n, pool_size, nullptr, 1, nullptr, w.ckey, w.crow, w.order_key,
+                                          w.owner, w.state, plans_out, n_plans_out);
     TD_LAUNCH_CHECK();
     return TD_OK;
 }
@@ -798,12 +884,9 @@ extern "C" int td_pool_merge_padded(const int32_t *slot_plans, const int32_t *sl
     if (total == 0) { TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st)); return TD_OK; }
     if (!slot_plans || !slot_counts || !plans_out || !workspace) return TD_ERR_INVALID;
     if (workspace_bytes < td_pool_merge_workspace_bytes(total, n)) return TD_ERR_WORKSPACE;
-    Carver c(workspace);
-    int32_t *order_key = c.take<int32_t>(total);
-    int32_t *owner = c.take<int32_t>(n > 0 ? n : 1);
-    uint8_t *state = c.take<uint8_t>(total);
-    pool_merge_kernel<<<1, 1024, 0, st>>>(slot_plans, total, n, pool_size, slot_counts, cap, slot_shard, order_key, owner, state,
-                                          plans_out, n_plans_out);
+    MergeWs w = carve_merge(workspace, total, n);
+    pool_merge_kernel<<<1, 1024, 0, st>>>(slot_plans, total, n, pool_size, slot_counts, cap, slot_shard, w.ckey, w.crow,
+                                          w.order_key, w.owner, w.state, plans_out, n_plans_out);
     TD_LAUNCH_CHECK();
     return TD_OK;
 }

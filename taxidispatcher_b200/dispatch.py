@@ -27,7 +27,8 @@ from . import _lib
 from ._lib import BIG_COST, INT32_MAX, POOL_REC_W, AssignStats, LcmParams, PoolStats, TaxiDispatchError, check
 
 __all__ = ["BIG_COST", "Engine", "calculate_cost", "solve", "solve_dispatch", "solve_full", "LCM", "LCM_heuristic",
-           "LCM_split", "LCM_greedy_opt", "LCM_simulate", "LCM_java", "find_pool", "find_pool_all", "pool_merge",
+           "LCM_split", "LCM_greedy_opt", "LCM_simulate", "LCM_java", "find_pool", "find_pool_all", "find_pool_block",
+           "pool_merge",
            "TaxiDispatchError"]
 
 
@@ -153,6 +154,37 @@ class Engine:
             check(rc, "td_pool_find")
             return out, cnt, (st if want_stats else None)
         raise TaxiDispatchError(_lib.TD_ERR_CAPACITY, "td_pool_find")
+
+    def pool_find_shards(self, demand: torch.Tensor, dist: torch.Tensor, pool_size: int, shard_begin: int = 0,
+                         shard_count: int = 8, n_shards: int = 8, max_feasible: Optional[int] = None,
+                         out: Optional[torch.Tensor] = None, counts_out: Optional[torch.Tensor] = None,
+                         want_stats: bool = True):
+        """Consecutive logical shards in one call (one enumeration + one selection launch for all of them).
+        out: [shard_count, cap, 9]; counts_out: [shard_count] int32 (device).  Returns (out, counts, stats list)."""
+        n = int(demand.shape[0])
+        n_stands = int(dist.shape[0])
+        cap = n // 2 + 1
+        if out is None:
+            out = torch.empty((shard_count, cap, POOL_REC_W), dtype=torch.int32, device=self.device)
+        cnt = counts_out if counts_out is not None else torch.zeros(shard_count, dtype=torch.int32, device=self.device)
+        key = ("pool_mf", n, pool_size, shard_count)
+        mf = int(max_feasible) if max_feasible is not None else self._ws.get(key, (1 << 21) * min(shard_count, 4))
+        for _ in range(8):
+            nbytes = self.lib.td_pool_shards_workspace_bytes(n, n_stands, pool_size, shard_count, mf)
+            ws = self._workspace(("pool", n, n_stands, pool_size, shard_count), nbytes)
+            st = (PoolStats * shard_count)()
+            rc = self.lib.td_pool_find_shards(_ptr(demand), n, _ptr(dist), n_stands, pool_size, shard_begin, shard_count,
+                                              n_shards, _ptr(out), int(out.shape[1]), _ptr(cnt),
+                                              st if want_stats else None, _ptr(ws), ws.numel(), mf, _stream())
+            if rc == _lib.TD_ERR_CAPACITY and want_stats:
+                need = sum(int(s.feasible) for s in st)
+                if need > mf:
+                    mf = need + 1024                      # grow the materialised list and retry
+                    self._ws[key] = mf
+                    continue
+            check(rc, "td_pool_find_shards")
+            return out, cnt, (list(st) if want_stats else None)
+        raise TaxiDispatchError(_lib.TD_ERR_CAPACITY, "td_pool_find_shards")
 
     def pool_merge(self, shard_plans: torch.Tensor, total: int, n: int, pool_size: int):
         out = torch.empty((max(total, 1), POOL_REC_W), dtype=torch.int32, device=self.device)
@@ -298,6 +330,21 @@ def find_pool(demand, dist, pool_size: int, shard: int = 0, n_shards: int = 8):
                                    "rounds": st.rounds, "passes": st.passes}
 
 
+def find_pool_block(demand, dist, pool_size: int, shard_begin: int, shard_count: int, n_shards: int = 8):
+    """Consecutive logical shards in one device call.  Returns [(plans, stats dict)] per shard."""
+    if shard_count <= 0:
+        return []
+    eng = engine()
+    dem = _h2d_i32(np.asarray(demand, dtype=np.int32).reshape(-1, 5))
+    d = _h2d_i32(dist)
+    out, cnt, st = eng.pool_find_shards(dem, d, pool_size, shard_begin, shard_count, n_shards)
+    counts = cnt.cpu().numpy()
+    plans = out.cpu().numpy()
+    return [(plans[s, : int(counts[s])].copy(),
+             {"evaluated": st[s].evaluated, "feasible": st[s].feasible, "kept": st[s].kept, "rounds": st[s].rounds,
+              "passes": st[s].passes}) for s in range(shard_count)]
+
+
 def pool_merge(shard_plans, n: int, pool_size: int):
     """findpool.c:83-108 on shard outputs given in shard order."""
     eng = engine()
@@ -316,19 +363,20 @@ def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
     n = dem_np.shape[0]
     dem = _h2d_i32(dem_np)
     d = _h2d_i32(dist)
-    cap = n // 2 + 1
-    allp = torch.empty((cap * n_shards, POOL_REC_W), dtype=torch.int32, device=eng.device)
-    total = 0
     stats = {"evaluated": 0, "feasible": 0, "kept_per_shard": [], "rounds": 0}
-    for sh in range(n_shards):
-        out, cnt, st = eng.pool_find(dem, d, pool_size, sh, n_shards, out=allp[total: total + cap])
-        m = int(cnt.item())
-        total += m
-        stats["evaluated"] += st.evaluated
-        stats["feasible"] += st.feasible
-        stats["rounds"] += st.rounds
-        stats["kept_per_shard"].append(m)
-    merged, cnt = eng.pool_merge(allp, total, n, pool_size)
+    parts, counts = [], []
+    for b in range(0, n_shards, 64):                       # one call serves up to 64 consecutive shards
+        cnt_sh = min(64, n_shards - b)
+        out, cnt, st = eng.pool_find_shards(dem, d, pool_size, b, cnt_sh, n_shards)
+        parts.append(out)
+        counts.append(cnt)
+        stats["evaluated"] += sum(int(s.evaluated) for s in st)
+        stats["feasible"] += sum(int(s.feasible) for s in st)
+        stats["rounds"] += int(st[0].rounds)
+        stats["kept_per_shard"] += [int(s.kept) for s in st]
+    slot_plans = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+    slot_counts = counts[0] if len(counts) == 1 else torch.cat(counts, dim=0)
+    merged, cnt = eng.pool_merge_padded(slot_plans, slot_counts, None, n, pool_size)
     m = int(cnt.item())
     stats["kept"] = m
     return merged[:m].cpu().numpy(), stats

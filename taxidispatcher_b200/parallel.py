@@ -5,8 +5,8 @@ collective inside any kernel -- the only exchange is the reference's own: gather
 survivors, then re-run the greedy scan on the concatenation (findpool.c:149-172).
 
   pool      the 8 LOGICAL shards of pool_n.c:226-229 are kept whatever the GPU count (the result
-            depends on them: each shard dedups before the merge); rank r runs logical shards
-            r, r+W, r+2W, ...; one all_gather of fixed-capacity survivor buffers; every rank (or
+            depends on them: each shard dedups before the merge); rank r runs a contiguous block
+            of logical shards; one all_gather of fixed-capacity survivor buffers; every rank (or
             rank 0 only) merges in shard order.
   cost      contiguous cab-row blocks per rank (rows_for_rank); no exchange.
   assign    independent instances (split.py ranges, per-minute batches) round-robin over ranks.
@@ -34,8 +34,10 @@ def world() -> Tuple[int, int]:
 
 
 def shards_for_rank(rank: int, world_size: int, n_shards: int = REF_SHARDS) -> List[int]:
-    """Logical shards owned by `rank` (round-robin, so that 8 shards balance over 1/2/4/8 ranks)."""
-    return list(range(rank, n_shards, world_size))
+    """Logical shards owned by `rank`: a CONTIGUOUS block (balanced to within one shard), so that one
+    td_pool_find_shards call serves all of a rank's shards."""
+    lo, hi = rows_for_rank(n_shards, rank, world_size)
+    return list(range(lo, hi))
 
 
 def rows_for_rank(n_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -90,17 +92,21 @@ def find_pool_sharded(demand, dist_table, pool_size: int, n_shards: int = REF_SH
                       compute_shard: Optional[Callable] = None, merge: Optional[Callable] = None):
     """`findpool` over the ranks of the current process group: returns (merged plans, stats) on every
     rank.  stats carry the sums over all logical shards (evaluated, feasible) and kept_per_shard."""
-    if compute_shard is None or merge is None:
-        from . import dispatch
-        compute_shard = compute_shard or dispatch.find_pool
-        merge = merge or dispatch.pool_merge
     rank, w = world()
     dem = np.asarray(demand, dtype=np.int32).reshape(-1, 5)
     n = dem.shape[0]
+    mine = shards_for_rank(rank, w, n_shards)
+    if compute_shard is None:
+        from . import dispatch                      # product path: one device call for the whole block
+        results = dispatch.find_pool_block(dem, dist_table, pool_size, mine[0], len(mine), n_shards) if mine else []
+    else:
+        results = [compute_shard(dem, dist_table, pool_size, sh, n_shards) for sh in mine]
+    if merge is None:
+        from . import dispatch
+        merge = dispatch.pool_merge
     local = []
     ev = fe = 0
-    for sh in shards_for_rank(rank, w, n_shards):
-        plans, st = compute_shard(dem, dist_table, pool_size, sh, n_shards)
+    for sh, (plans, st) in zip(mine, results):
         local.append((sh, plans))
         ev += int(st["evaluated"])
         fe += int(st["feasible"])

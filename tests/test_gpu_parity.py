@@ -279,3 +279,27 @@ def test_assign_optimum_not_above_lcm(td):
     C = g.config2()[:400, :400].copy()
     _, _, obj, _ = td.solve_full(400, C)
     assert obj <= td.LCM_heuristic(400, C)
+
+
+def test_pool_batched_shards_match_single_shard_calls(td):
+    """td_pool_find_shards: several consecutive logical shards in one enumeration + one selection launch"""
+    gold = load_golden("pool722.json")
+    dem = g.pool_demand()
+    dist = g.stand_distances(50)
+    for begin, count in ((0, 8), (2, 3), (7, 1)):
+        res = td.find_pool_block(dem, dist, 4, begin, count, 8)
+        assert len(res) == count
+        for s, (plans, st) in enumerate(res):
+            gs = gold["shards"][begin + s]
+            assert plans.tolist() == gs["plans"], (begin, s)
+            assert {q: st[q] for q in ("evaluated", "feasible", "kept")} == gs["stats"]
+    merged, stats = td.find_pool_all(dem, dist, 4)
+    assert merged.tolist() == gold["merged"]
+    assert stats["evaluated"] == sum(g.POOL722_EVALUATED) and stats["kept_per_shard"] == g.POOL722_KEPT
+    # ragged: more shards than leaders, pool size 3, odd shard count
+    dem2 = g.pool_demand(45, seed=4)
+    d51 = g.stand_distances(51)
+    for n_shards in (5, 64):
+        m, st = td.find_pool_all(dem2, d51, 3, n_shards=n_shards)
+        ref = pool_ref.merge([pool_ref.find(dem2, d51, 3, sh, n_shards)[0] for sh in range(n_shards)], 45, 3)
+        assert np.array_equal(m, ref), n_shards
