@@ -303,3 +303,34 @@ def test_pool_batched_shards_match_single_shard_calls(td):
         m, st = td.find_pool_all(dem2, d51, 3, n_shards=n_shards)
         ref = pool_ref.merge([pool_ref.find(dem2, d51, 3, sh, n_shards)[0] for sh in range(n_shards)], 45, 3)
         assert np.array_equal(m, ref), n_shards
+
+
+# ---- file / CLI protocols ------------------------------------------------------------
+def test_cli_twins_speak_the_reference_file_protocols(td, tmp_path, monkeypatch):
+    import os
+    from taxidispatcher_b200 import formats
+    from taxidispatcher_b200.cli import findpool, pool_n, solver
+    case = [c for c in load_golden("pool_small.json") if c["label"] == "n180_seed11_k4"][0]
+    dem = np.array(case["demand"], dtype=np.int32)
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "demand.csv").write_text(formats.write_demand_csv(dem))
+    # pool_n <pool-size> <thread> <demand-file> <rec-number> <output-file>   (pool_n.c:211-219)
+    for sh in (0, 3, 7):
+        assert pool_n.main(["4", str(sh), "demand.csv", str(len(dem)), "out%d.csv" % sh]) == 0
+        assert os.path.exists("out%d.flg" % sh)                                   # pool_n.c:56-62
+        got = formats.read_result_csv((tmp_path / ("out%d.csv" % sh)).read_text(), 4)
+        assert got.tolist() == case["shards"][sh]["plans"]
+        assert (tmp_path / ("out%d.csv" % sh)).read_text() == pool_ref.format_result_csv(np.array(case["shards"][sh]["plans"]), 4)
+    assert pool_n.main(["4", "0", "missing.csv", "10", "o.csv"]) == 1            # pool_n.c:36-39
+    assert pool_n.main(["4", "0"]) == 1                                           # usage
+    # findpool <pool-size> <demand-file> <rec-number> <output-file>           (findpool.c:127-134)
+    assert findpool.main(["4", "demand.csv", str(len(dem)), "pool_out.csv"]) == 0
+    merged = formats.read_result_csv((tmp_path / "pool_out.csv").read_text(), 4)
+    assert merged[:, :8].tolist() == [r[:8] for r in case["merged"]]
+    # solver.py: cost.txt -> solv_out.txt                                      (solver.py:30-39)
+    C = g.config1a(60)
+    (tmp_path / "cost.txt").write_text(formats.write_cost_txt(C))
+    assert solver.main(["cost.txt", "solv_out.txt"]) == 0
+    x = formats.read_solv_out((tmp_path / "solv_out.txt").read_text(), 60)
+    assert assign_ref.check_x(x, 60)
+    assert int((C.reshape(-1) * x).sum()) == assign_ref.solve_scipy(C)[0]
