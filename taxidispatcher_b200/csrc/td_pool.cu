@@ -66,13 +66,16 @@ constexpr int kMaxBands = 8;      // cost bands of the selection; band sizes gro
 constexpr unsigned kBand0 = 4096;
 
 struct PoolCtrl {
+    // ---- persistent over the passes of one call ----
     unsigned long long tstamp[32];  // %globaltimer at the phase boundaries of pool_select (diagnostics)
     unsigned long long evaluated[kMaxSlots], feasible[kMaxSlots];  // per logical shard of this call
     unsigned int n_kept[kMaxSlots];
+    unsigned int total_rounds;
+    unsigned int n_items;         // work items of the enumeration (set once by pool_item_offsets)
+    unsigned int pass_begin_marker;  // ---- everything below is zeroed before every enumeration pass ----
     unsigned int n_records;       // slots reserved in the record list
     unsigned int item_counter;
     unsigned int overflow;
-    unsigned int n_items;
     unsigned int rounds;
     int band_hi[kMaxSlots][kMaxBands];           // exclusive cost bound of band b for each logical shard
     unsigned int band_cnt[kMaxSlots][kMaxBands]; // records of shard s in band b (from the histogram)
@@ -182,6 +185,12 @@ struct EnumArgs {
     const unsigned int *item_off; PoolRec *recs; PoolCtrl *ctrl;
     int n, S, start, stop; unsigned int cap;
     int step, shard_begin;        // leader p0 belongs to call slot p0 / step - shard_begin
+    // multi-pass support (large inputs): only plans with cost in [cost_lo, cost_hi) are materialised, customers
+    // whose alive flag is 0 (taken by an earlier cost window) are pruned at every pickup level
+    int cost_lo, cost_hi;
+    const uint8_t *alive;         // [shard_count x n] or NULL (first pass: everybody is free)
+    int count_stats;              // accumulate evaluated / feasible (first pass only)
+    int item_stride;              // > 1: sampling pass -- every item_stride-th item, histogram only
 };
 
 template <bool kDistSmem>
@@ -203,9 +212,11 @@ struct WarpOut {  // per-warp slice of the record list
 
 __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, bool has, unsigned long long rank, int cost,
                                              int lane, unsigned *whist) {
+    has = has && cost >= a.cost_lo;                 // earlier windows are done
+    if (has) atomicAdd(&whist[cost < 0 ? 0 : (cost < kBuckets ? cost : kBuckets - 1)], 1u);
+    has = has && cost < a.cost_hi && a.item_stride == 1;
     const unsigned ball = __ballot_sync(0xffffffffu, has);
     if (ball == 0) return;
-    if (has) atomicAdd(&whist[cost < kBuckets ? cost : kBuckets - 1], 1u);
     const unsigned need = __popc(ball);
     if (wo.used + need > kChunk) {
         // abandon the rest of the current chunk (mark holes) and reserve a new one
@@ -320,7 +331,7 @@ pool_enum_kernel(EnumArgs a) {
             my_eval += __shfl_xor_sync(0xffffffffu, my_eval, o);
             my_feas += __shfl_xor_sync(0xffffffffu, my_feas, o);
         }
-        if (lane == 0 && cur_slot >= 0) {
+        if (lane == 0 && cur_slot >= 0 && a.count_stats) {
             if (my_eval) atomicAdd(&a.ctrl->evaluated[cur_slot], my_eval);
             if (my_feas) atomicAdd(&a.ctrl->feasible[cur_slot], my_feas);
         }
@@ -331,7 +342,8 @@ pool_enum_kernel(EnumArgs a) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(&a.ctrl->item_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_items) break;
+        if (item >= (n_items + unsigned(a.item_stride) - 1) / unsigned(a.item_stride)) break;
+        item *= unsigned(a.item_stride);
         // leader = last index with item_off[idx] <= item
         int lo = 0, hi = n_lead;
         while (hi - lo > 1) {
@@ -342,6 +354,8 @@ pool_enum_kernel(EnumArgs a) {
         const int4 c0 = cust[p0];
         const int slot = p0 / a.step - a.shard_begin;
         if (slot != cur_slot) { flush_counts(); cur_slot = slot; }
+        const uint8_t *al = a.alive ? a.alive + size_t(slot) * n : nullptr;
+        if (al && !al[p0]) continue;
 
         if (K == 2) {
             // lanes over p1
@@ -349,7 +363,7 @@ pool_enum_kernel(EnumArgs a) {
             for (int t1 = lane; t1 < ((n1 + 31) & ~31); t1 += 32) {
                 bool valid = t1 < n1;
                 int p1 = 0;
-                if (valid) { p1 = a.list[size_t(c0.x) * n + t1]; valid = p1 != p0; }
+                if (valid) { p1 = a.list[size_t(c0.x) * n + t1]; valid = p1 != p0 && (!al || al[p1]); }
                 int nfeas = 0, best = INT_MAX;
                 if (valid) {
                     const int4 c1 = cust[p1];
@@ -374,7 +388,7 @@ pool_enum_kernel(EnumArgs a) {
 
         const int t1 = int(item - a.item_off[lo]);
         const int p1 = a.list[size_t(c0.x) * n + t1];
-        if (p1 == p0) continue;
+        if (p1 == p0 || (al && !al[p1])) continue;
         const int4 c1 = cust[p1];
         const int a01 = D(c0.x, c1.x);  // <= W[p1] by construction of the prefix
         const int t01 = D(c0.y, c1.y), t10 = D(c1.y, c0.y);
@@ -386,7 +400,7 @@ pool_enum_kernel(EnumArgs a) {
                 int p2 = 0;
                 if (valid) {
                     p2 = a.list[size_t(c1.x) * n + t2];
-                    valid = p2 != p0 && p2 != p1 && (a01 < kTbl || a.slack[size_t(c1.x) * n + t2] >= a01);
+                    valid = p2 != p0 && p2 != p1 && (a01 < kTbl || a.slack[size_t(c1.x) * n + t2] >= a01) && (!al || al[p2]);
                 }
                 int nfeas = 0, best = INT_MAX;
                 if (valid) {
@@ -412,7 +426,7 @@ pool_enum_kernel(EnumArgs a) {
         const int n2 = cand_count(a.cnt, c1.x, a01);
         for (int t2 = 0; t2 < n2; ++t2) {
             const int p2 = a.list[size_t(c1.x) * n + t2];
-            if (p2 == p0 || p2 == p1) continue;
+            if (p2 == p0 || p2 == p1 || (al && !al[p2])) continue;
             if (a01 >= kTbl && a.slack[size_t(c1.x) * n + t2] < a01) continue;
             const int4 c2 = cust[p2];
             const int a12 = D(c1.x, c2.x);
@@ -424,7 +438,8 @@ pool_enum_kernel(EnumArgs a) {
                 int p3 = 0;
                 if (valid) {
                     p3 = a.list[size_t(c2.x) * n + t3];
-                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2 < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2);
+                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2 < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2) &&
+                            (!al || al[p3]);
                 }
                 int nfeas = 0, best = INT_MAX;
                 if (valid) {
@@ -458,6 +473,8 @@ struct SelArgs {
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolRec *kept;
     int n, K;
     int n_slots, step, shard_begin, keep_cap;   // per-slot state lives at [slot * n + customer]
+    int first_pass;                             // 1: every customer starts free; 0: keep alive[] from the earlier windows
+    int cost_hi;                                // records with cost >= cost_hi were counted in hist but not materialised
 };
 
 __device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
@@ -488,7 +505,7 @@ pool_select_kernel(SelArgs a) {
     __shared__ int s_band_hi[kMaxSlots][kMaxBands];
     const unsigned n_state = unsigned(n) * unsigned(a.n_slots);
     for (unsigned c = tid; c < n_state; c += nthreads) {
-        a.alive[c] = 1;
+        if (a.first_pass) a.alive[c] = 1;
         a.best_hi[0][c] = a.best_hi[1][c] = ~0ull;
         a.best_lo[0][c] = a.best_lo[1][c] = ~0u;
     }
@@ -497,7 +514,7 @@ pool_select_kernel(SelArgs a) {
         unsigned in_band = 0;
         int band = 0;
         for (int bkt = 0; bkt < kBuckets; ++bkt) {
-            const unsigned h = ctrl->hist[tid][bkt];
+            const unsigned h = bkt < a.cost_hi ? ctrl->hist[tid][bkt] : 0u;
             cum += h; in_band += h;
             if (band < kMaxBands - 1 && bkt < kBuckets - 1 && cum >= target) {
                 ctrl->band_hi[tid][band] = bkt + 1;
@@ -713,7 +730,7 @@ pool_select_kernel(SelArgs a) {
         }
         stamp();
     }
-    if (tid == 0) ctrl->rounds = rounds;
+    if (tid == 0) { ctrl->rounds = rounds; ctrl->total_rounds += rounds; }
 }
 
 // kept plans -> ascending (cost, rank) -> pool_n.c:123-134 records
@@ -897,6 +914,12 @@ static PoolWorkspace carve_pool(void *ws, int n, int S, int n_slots, int64_t max
 // chunked reservation can strand up to one chunk per resident warp
 static int64_t record_slack() { return int64_t(kChunk) * 148 * 64; }
 
+#define TDH_RC_LOCAL(expr)      \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc != TD_OK) return _rc; \
+    } while (0)
+
 template <int K>
 static int launch_enum(const EnumArgs &a, int grid, cudaStream_t st) {
     const size_t dist_b = (size_t(a.S) * a.S * 4 + 15) & ~size_t(15);
@@ -968,54 +991,142 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
     pool_item_offsets_kernel<<<1, 1024, 0, st>>>(w.cust, w.cnt, start, stop, pool_size, w.item_off, w.ctrl);
     TD_LAUNCH_CHECK();
 
-    EnumArgs ea;
-    ea.cust = w.cust; ea.dist = dist; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
-    ea.recs = w.recs[0]; ea.ctrl = w.ctrl; ea.n = n; ea.S = n_stands; ea.start = start; ea.stop = stop;
-    ea.cap = unsigned(rec_cap64); ea.step = step; ea.shard_begin = shard_begin;
     const int sms = device_sm_count();
-    const int grid = sms * 4;
-    int rc;
-    {
-        ProfScope prof(TD_PROF_POOL_ENUM, st);
-        rc = pool_size == 4 ? launch_enum<4>(ea, grid, st) : pool_size == 3 ? launch_enum<3>(ea, grid, st) : launch_enum<2>(ea, grid, st);
-    }
-    if (rc != TD_OK) return rc;
+    int sel_per_sm = 0;
+    TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sel_per_sm, pool_select_kernel, kSelThreads, 0));
+    if (sel_per_sm < 1) return TD_ERR_CUDA;
+    sel_per_sm = sel_per_sm > 4 ? 4 : sel_per_sm;
+    if (sms * sel_per_sm < shard_count) return TD_ERR_INVALID;
 
-    SelArgs sa;
-    sa.list[0] = w.recs[0]; sa.list[1] = w.recs[1]; sa.act[0] = w.act[0]; sa.act[1] = w.act[1]; sa.ctrl = w.ctrl;
-    sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
-    sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = pool_size;
-    sa.n_slots = shard_count; sa.step = step; sa.shard_begin = shard_begin; sa.keep_cap = keep_cap;
-    int per_sm = 0;
-    TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_select_kernel, kSelThreads, 0));
-    if (per_sm < 1) return TD_ERR_CUDA;
-    per_sm = per_sm > 4 ? 4 : per_sm;
-    if (sms * per_sm < shard_count) return TD_ERR_INVALID;
-    void *sargs[] = {(void *)&sa};
-    {
-        ProfScope prof(TD_PROF_POOL_SELECT, st);
-        TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)pool_select_kernel, dim3(sms * per_sm), dim3(kSelThreads), sargs, 0, st));
+    // the per-pass part of the control block (everything after pass_begin_marker)
+    const size_t pass_off = offsetof(PoolCtrl, pass_begin_marker);
+    auto reset_pass = [&]() -> int {
+        TD_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<char *>(w.ctrl) + pass_off, 0, sizeof(PoolCtrl) - pass_off, st));
+        return TD_OK;
+    };
+    auto run_enum = [&](int cost_lo, int cost_hi, bool use_alive, bool count_stats, int stride) -> int {
+        EnumArgs ea;
+        ea.cust = w.cust; ea.dist = dist; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
+        ea.recs = w.recs[0]; ea.ctrl = w.ctrl; ea.n = n; ea.S = n_stands; ea.start = start; ea.stop = stop;
+        ea.cap = unsigned(rec_cap64); ea.step = step; ea.shard_begin = shard_begin;
+        ea.cost_lo = cost_lo; ea.cost_hi = cost_hi; ea.alive = use_alive ? w.alive : nullptr;
+        ea.count_stats = count_stats ? 1 : 0; ea.item_stride = stride;
+        ProfScope prof(TD_PROF_POOL_ENUM, st);
+        return pool_size == 4 ? launch_enum<4>(ea, sms * 4, st) : pool_size == 3 ? launch_enum<3>(ea, sms * 4, st)
+                                                                                   : launch_enum<2>(ea, sms * 4, st);
+    };
+    auto run_select = [&](bool first, int window_hi) -> int {
+        SelArgs sa;
+        sa.list[0] = w.recs[0]; sa.list[1] = w.recs[1]; sa.act[0] = w.act[0]; sa.act[1] = w.act[1]; sa.ctrl = w.ctrl;
+        sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
+        sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = pool_size;
+        sa.n_slots = shard_count; sa.step = step; sa.shard_begin = shard_begin; sa.keep_cap = keep_cap;
+        sa.first_pass = first ? 1 : 0;
+        sa.cost_hi = window_hi;
+        void *sargs[] = {(void *)&sa};
+        {
+            ProfScope prof(TD_PROF_POOL_SELECT, st);
+            TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)pool_select_kernel, dim3(sms * sel_per_sm), dim3(kSelThreads), sargs, 0, st));
+        }
+        count_launch();
+        return TD_OK;
+    };
+
+    static thread_local PoolCtrl h;
+    int passes = 0;
+    if (!stats) {
+        // asynchronous single pass: no host round trip; an overflow is reported through counts_out[s] = -1
+        int rc = run_enum(INT_MIN, INT_MAX, false, true, 1);
+        if (rc != TD_OK) return rc;
+        rc = run_select(true, INT_MAX);
+        if (rc != TD_OK) return rc;
+        pool_emit_kernel<<<shard_count, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, keep_cap, plans_out, cap, counts_out);
+        TD_LAUNCH_CHECK();
+        return TD_OK;
     }
-    count_launch();
+
+    // synchronous path: cost windows.  Window 0 tries to take everything; when the record list would overflow,
+    // the histogram (which keeps counting after an overflow) tells where to cut, and later windows only
+    // enumerate customers that are still free.
+    unsigned n_items_host = 0;
+    TD_CUDA_TRY(cudaMemcpyAsync(&n_items_host, &w.ctrl->n_items, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    TD_CUDA_TRY(cudaStreamSynchronize(st));
+    const double budget = 0.9 * double(max_feasible);
+    auto cut_from_hist = [&](int lo_bucket, double scale) -> int {   // largest cost bound whose cumulative count fits
+        double cum = 0;
+        int hi = lo_bucket;
+        for (int bkt = lo_bucket; bkt < kBuckets - 1; ++bkt) {
+            double c = 0;
+            for (int sl = 0; sl < shard_count; ++sl) c += h.hist[sl][bkt];
+            if (cum + c * scale > budget) break;
+            cum += c * scale;
+            hi = bkt + 1;
+        }
+        return hi;
+    };
+    int cost_lo = INT_MIN;
+    bool first_select = true, stats_counted = false;
+    for (int guard = 0; guard < 4 * kBuckets; ++guard) {
+        int cost_hi = INT_MAX;
+        const bool use_alive = !first_select;
+        // big inputs: a 1/64 sampling pass estimates the histogram so that the full pass does not overflow
+        const bool sample = (long long)n_items_host > (1ll << 21);
+        if (sample) {
+            TDH_RC_LOCAL(reset_pass());
+            int rc = run_enum(cost_lo, INT_MAX, use_alive, false, 64);
+            if (rc != TD_OK) return rc;
+            ++passes;
+            TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
+            TD_CUDA_TRY(cudaStreamSynchronize(st));
+            double tot = 0;
+            for (int sl = 0; sl < shard_count; ++sl) for (int bkt = 0; bkt < kBuckets; ++bkt) tot += h.hist[sl][bkt];
+            if (tot * 64.0 * 1.3 > budget) {
+                const int lo_b = cost_lo == INT_MIN ? 0 : (cost_lo < kBuckets ? cost_lo : kBuckets - 1);
+                const int cut = cut_from_hist(lo_b, 64.0 * 1.3);
+                if (cut > lo_b) cost_hi = cut;   // else: a single cost level is too big for the estimate, try anyway
+            }
+        }
+        for (;;) {   // full pass, shrinking the window if it still overflows
+            TDH_RC_LOCAL(reset_pass());
+            int rc = run_enum(cost_lo, cost_hi, use_alive, !stats_counted, 1);
+            if (rc != TD_OK) return rc;
+            ++passes;
+            stats_counted = true;
+            TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
+            TD_CUDA_TRY(cudaStreamSynchronize(st));
+            if (!h.overflow) break;
+            const int lo_b = cost_lo == INT_MIN ? 0 : (cost_lo < kBuckets ? cost_lo : kBuckets - 1);
+            const int cut = cut_from_hist(lo_b, 1.0);
+            if (cut <= lo_b || (cost_hi != INT_MAX && cut >= cost_hi)) {
+                // one cost level alone exceeds the record capacity: the caller has to provide a bigger workspace
+                for (int sl = 0; sl < shard_count; ++sl) {
+                    stats[sl].evaluated = int64_t(h.evaluated[sl]); stats[sl].feasible = int64_t(h.feasible[sl]);
+                    stats[sl].passes = passes;
+                }
+                return TD_ERR_CAPACITY;
+            }
+            cost_hi = cut;
+        }
+        int rc = run_select(first_select, cost_hi);
+        if (rc != TD_OK) return rc;
+        first_select = false;
+        if (cost_hi == INT_MAX) break;
+        cost_lo = cost_hi;
+    }
     pool_emit_kernel<<<shard_count, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, keep_cap, plans_out, cap, counts_out);
     TD_LAUNCH_CHECK();
-
-    if (stats) {
-        static thread_local PoolCtrl h;
-        TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
-        TD_CUDA_TRY(cudaStreamSynchronize(st));
-        bool over_cap = false;
-        for (int s = 0; s < shard_count; ++s) {
-            stats[s].evaluated = int64_t(h.evaluated[s]);
-            stats[s].feasible = int64_t(h.feasible[s]);
-            stats[s].kept = h.n_kept[s];
-            stats[s].rounds = int32_t(h.rounds);
-            stats[s].passes = 1;
-            over_cap = over_cap || int64_t(h.n_kept[s]) > cap;
-        }
-        if (h.overflow || over_cap) return TD_ERR_CAPACITY;
+    TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, offsetof(PoolCtrl, pass_begin_marker), cudaMemcpyDeviceToHost, st));
+    TD_CUDA_TRY(cudaStreamSynchronize(st));
+    bool over_cap = false;
+    for (int sl = 0; sl < shard_count; ++sl) {
+        stats[sl].evaluated = int64_t(h.evaluated[sl]);
+        stats[sl].feasible = int64_t(h.feasible[sl]);
+        stats[sl].kept = h.n_kept[sl];
+        stats[sl].rounds = int32_t(h.total_rounds);
+        stats[sl].passes = passes;
+        over_cap = over_cap || int64_t(h.n_kept[sl]) > cap;
     }
-    return TD_OK;
+    return over_cap ? TD_ERR_CAPACITY : TD_OK;
 }
 
 extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size, int shard,

@@ -334,3 +334,28 @@ def test_cli_twins_speak_the_reference_file_protocols(td, tmp_path, monkeypatch)
     x = formats.read_solv_out((tmp_path / "solv_out.txt").read_text(), 60)
     assert assign_ref.check_x(x, 60)
     assert int((C.reshape(-1) * x).sum()) == assign_ref.solve_scipy(C)[0]
+
+
+def test_pool_multi_pass_cost_windows(td):
+    """A record capacity far below the feasible count forces the cost-window passes (later windows
+    enumerate only customers that are still free); results must not change."""
+    import torch
+    gold = load_golden("pool722.json")
+    eng = td.engine()
+    dem = torch.from_numpy(g.pool_demand()).cuda()
+    dist = torch.from_numpy(g.stand_distances(50)).cuda()
+    out, cnt, st = eng.pool_find_shards(dem, dist, 4, 0, 8, 8, max_feasible=600_000)   # ~16 M feasible plans in total
+    counts = cnt.cpu().numpy()
+    assert max(s.passes for s in st) >= 3
+    for s in range(8):
+        assert out[s, : counts[s]].cpu().numpy().tolist() == gold["shards"][s]["plans"], s
+        assert (st[s].evaluated, st[s].feasible, st[s].kept) == tuple(gold["shards"][s]["stats"][q] for q in ("evaluated", "feasible", "kept"))
+    # small ragged case, pool sizes 2..4, tiny capacity
+    case_dem = np.array(load_golden("pool_small.json")[3]["demand"], dtype=np.int32)
+    d51 = g.stand_distances(51)
+    for k in (2, 3, 4):
+        for sh in (0, 5):
+            o, c, s2 = eng.pool_find_shards(torch.from_numpy(case_dem).cuda(), torch.from_numpy(d51).cuda(), k, sh, 1, 8, max_feasible=64)
+            ref, rst = pool_ref.find(case_dem, d51, k, sh)
+            assert o[0, : int(c[0])].cpu().numpy().tolist() == ref.tolist(), (k, sh)
+            assert (s2[0].evaluated, s2[0].feasible) == (rst["evaluated"], rst["feasible"])
