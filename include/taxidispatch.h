@@ -173,6 +173,22 @@ int td_pool_find_shards(const int32_t *demand, int n, const int32_t *dist, int n
                         void *workspace, size_t workspace_bytes, int64_t max_feasible /* all shards together */,
                         void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 2-passenger pool of the Simulator      replaces Simulator.findPool (Simulator.java:681-758; pool.c:64-131)
+ *
+ * Customers are given by their from / to stands (from[i] < 0 marks a removed row, Simulator.java:688).
+ * Every ordered pair (A picked up first, then B) is a candidate; the cheaper of the two drop orders
+ * is its plan (pairs_out plan column: 1 = B ends / CLNT_B_ENDS, 0 = A ends).  accept_all != 0 keeps
+ * every pair -- the Simulator's actual behaviour (plan1 = plan2 = true at :691); accept_all == 0 applies
+ * the loss tests as written (:701-707) with max_loss (1.01).  Stable sort by cost, greedy disjoint scan.
+ * pairs_out rows: [custA, custB, plan, cost] in scan order.
+ * ------------------------------------------------------------------------------------------ */
+size_t td_pool_pairs_workspace_bytes(int n);
+int td_pool_pairs(const int32_t *from, const int32_t *to, int n, const int32_t *dist, int n_stands,
+                  int accept_all, double max_loss,
+                  int32_t *pairs_out /* cap x 4 */, int32_t cap, int32_t *n_pairs_out /* 1 */,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
 /* findpool.c:83-108: concatenated shard survivors (shard order) -> sort on column 8 -> greedy
  * disjoint scan.  Reference quirk kept: for pool_size < 4 findpool.c sorts on a column it never
  * filled (findpool.c:34-35,70), so the scan runs in concatenation order. */

@@ -226,3 +226,55 @@ int pool_oracle_merge(const int32_t *plans, int64_t total, int n_cust, int pool_
     *n_out = kept;
     return kept > cap ? -3 : 0;
 }
+
+/*
+ * 2-passenger pool of the Simulator: Simulator.java:681-758 (candidates :686-723, TimSort by cost :727,
+ * greedy scan :729-739).  accept_all != 0 reproduces `boolean plan1=true, plan2=true` (:691), i.e. what
+ * the reference really does (SURVEY.md section 4 trap 6); accept_all == 0 applies the tests as written.
+ * out rows: custA, custB, plan (1 = CLNT_B_ENDS, 0 = CLNT_A_ENDS), cost -- in scan order.
+ */
+int pool_pairs_oracle(const int32_t *from, const int32_t *to, int n, const int32_t *dist, int S, int accept_all,
+                      double max_loss, int32_t *out, int64_t cap, int64_t *n_out) {
+    int64_t total = (int64_t)n * n, m = 0;
+    int32_t *a = (int32_t *)malloc((size_t)(total ? total : 1) * 4 * sizeof(int32_t));
+    if (!a) return -1;
+#define DD(x, y) dist[(int64_t)(x) * S + (y)]
+    for (int A = 0; A < n; A++)
+        for (int B = 0; B < n; B++) {
+            if (A == B || from[A] < 0 || from[B] < 0) continue;
+            int plan1 = accept_all != 0, plan2 = accept_all != 0;
+            int cost1 = DD(from[A], from[B]) + DD(from[B], to[A]) + DD(to[A], to[B]);
+            int cost2 = DD(from[A], from[B]) + DD(from[B], to[B]) + DD(to[B], to[A]);
+            if (DD(from[B], to[A]) + DD(to[A], to[B]) < DD(from[B], to[B]) * max_loss &&
+                DD(from[A], from[B]) + DD(from[B], to[A]) < DD(from[A], to[A]) * max_loss) plan1 = 1;
+            if (cost2 < DD(from[A], to[A]) * max_loss) plan2 = 1;
+            if (plan1 || plan2) {
+                int32_t *r = a + m * 4;
+                r[0] = A; r[1] = B;
+                if (cost1 < cost2) { r[2] = 1; r[3] = cost1; } else { r[2] = 0; r[3] = cost2; }
+                m++;
+            }
+        }
+#undef DD
+    /* stable counting sort by cost */
+    int32_t hi = 0;
+    for (int64_t i = 0; i < m; i++) if (a[i * 4 + 3] > hi) hi = a[i * 4 + 3];
+    int64_t *cnt = (int64_t *)calloc((size_t)hi + 2, sizeof(int64_t));
+    int64_t *ord = (int64_t *)malloc((size_t)(m ? m : 1) * sizeof(int64_t));
+    uint8_t *used = (uint8_t *)calloc((size_t)n + 1, 1);
+    if (!cnt || !ord || !used) return -1;
+    for (int64_t i = 0; i < m; i++) cnt[a[i * 4 + 3] + 1]++;
+    for (int32_t v = 0; v <= hi; v++) cnt[v + 1] += cnt[v];
+    for (int64_t i = 0; i < m; i++) ord[cnt[a[i * 4 + 3]]++] = i;
+    int64_t kept = 0;
+    for (int64_t o = 0; o < m; o++) {
+        const int32_t *r = a + ord[o] * 4;
+        if (used[r[0]] || used[r[1]]) continue;
+        used[r[0]] = used[r[1]] = 1;
+        if (kept < cap) memcpy(out + kept * 4, r, 4 * sizeof(int32_t));
+        kept++;
+    }
+    free(a); free(cnt); free(ord); free(used);
+    *n_out = kept;
+    return kept > cap ? -3 : 0;
+}

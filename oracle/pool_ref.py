@@ -104,3 +104,20 @@ def format_result_csv(plans, pool_size):
     for r in np.asarray(plans).reshape(-1, REC_W):
         out.append("".join("%d," % int(v) for v in r[: 2 * pool_size]) + "%d,\n" % int(r[8]))
     return "".join(out)
+
+
+def pairs(frm, to, dist, accept_all=True, max_loss=1.01):
+    """Simulator.findPool restated (oracle/pool_oracle.c: pool_pairs_oracle)."""
+    f = np.ascontiguousarray(np.asarray(frm, dtype=np.int32))
+    t = np.ascontiguousarray(np.asarray(to, dtype=np.int32))
+    d = np.ascontiguousarray(np.asarray(dist, dtype=np.int32))
+    n = len(f)
+    out = np.zeros((n // 2 + 1, 4), dtype=np.int32)
+    cnt = ctypes.c_int64(0)
+    rc = _clib.lib().pool_pairs_oracle(f.ctypes.data_as(ctypes.c_void_p), t.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(n),
+                                       d.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(d.shape[0]),
+                                       ctypes.c_int(1 if accept_all else 0), ctypes.c_double(max_loss),
+                                       out.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(out)), ctypes.byref(cnt))
+    if rc != 0:
+        raise RuntimeError("pool_pairs_oracle rc=%d" % rc)
+    return out[: cnt.value].copy()

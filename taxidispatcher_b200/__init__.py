@@ -10,7 +10,7 @@ there is no CPU fallback.  Importing this package alone touches neither.
 __version__ = "0.1.0"
 
 _DISPATCH = ("BIG_COST", "Engine", "engine", "calculate_cost", "solve", "solve_dispatch", "solve_full", "LCM",
-             "LCM_heuristic", "LCM_split", "LCM_greedy_opt", "LCM_simulate", "LCM_java", "find_pool", "find_pool_all", "find_pool_block",
+             "LCM_heuristic", "LCM_split", "LCM_greedy_opt", "LCM_simulate", "LCM_java", "find_pool", "find_pool_all", "find_pool_block", "find_pool_pairs",
              "pool_merge", "TaxiDispatchError")
 
 

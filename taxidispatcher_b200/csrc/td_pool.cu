@@ -881,6 +881,74 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, co
     if (tid == 0) *n_plans_out = s_m;
 }
 
+// ---- 2-passenger pool of the Simulator (Simulator.java:681-758; pool.c:64-131) -----------------------
+// Every ordered pair (A,B), A != B, is a candidate: A is picked up first, then B; cost1 = B dropped last,
+// cost2 = A dropped last; the cheaper one is the pair's plan (ties -> A ends, Simulator.java:711-718).
+// The Simulator initialises plan1 = plan2 = true (:691), so its loss tests are dead and EVERY pair is kept
+// (SURVEY.md section 4 trap 6, the golden log was produced that way); accept_all = 0 applies the tests as
+// written (:701-707, the pool.c behaviour).  Selection = stable sort by cost + greedy disjoint scan
+// (:727-739) = the same dominance rounds with rank = A * n + B (TimSort is stable, candidates are A-major).
+__global__ void __launch_bounds__(256)
+pool_pairs_enum_kernel(const int32_t *__restrict__ from, const int32_t *__restrict__ to, int n,
+                       const int32_t *__restrict__ dist, int S, int accept_all, double max_loss, PoolRec *recs,
+                       PoolCtrl *ctrl) {
+    __shared__ unsigned s_hist[kBuckets];
+    for (int b = threadIdx.x; b < kBuckets; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    const long long total = (long long)n * n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int A = int(idx / n), B = int(idx - (long long)A * n);
+        PoolRec r; r.rank = 0; r.cost = -1; r.pad = 0;
+        const int fa = from[A], ta = to[A], fb = from[B], tb = to[B];
+        if (A != B && fa >= 0 && fb >= 0) {                       // id == -1 rows are skipped (:688)
+            const int dab = dist[size_t(fa) * S + fb];
+            const int cost1 = dab + dist[size_t(fb) * S + ta] + dist[size_t(ta) * S + tb];
+            const int cost2 = dab + dist[size_t(fb) * S + tb] + dist[size_t(tb) * S + ta];
+            bool ok = accept_all != 0;
+            if (!ok) {
+                const double dB = double(dist[size_t(fb) * S + tb]), dA = double(dist[size_t(fa) * S + ta]);
+                const bool plan1 = double(dist[size_t(fb) * S + ta] + dist[size_t(ta) * S + tb]) < __dmul_rn(dB, max_loss) &&
+                                   double(dab + dist[size_t(fb) * S + ta]) < __dmul_rn(dA, max_loss);
+                const bool plan2 = double(cost2) < __dmul_rn(dA, max_loss);
+                ok = plan1 || plan2;
+            }
+            if (ok) {
+                const int plan = cost1 < cost2 ? 1 : 0;             // CLNT_B_ENDS = 1, CLNT_A_ENDS = 0
+                r.cost = cost1 < cost2 ? cost1 : cost2;
+                r.rank = make_rank(A, B, 0, 0, plan);
+                atomicAdd(&s_hist[r.cost < kBuckets ? r.cost : kBuckets - 1], 1u);
+            }
+        }
+        recs[idx] = r;                                              // dense layout, holes have cost -1
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kBuckets; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(&ctrl->hist[0][b], s_hist[b]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->n_records = unsigned(total);
+}
+
+// kept pairs in (cost, A*n+B) order -> rows [custA, custB, plan, cost]
+__global__ void __launch_bounds__(1024)
+pool_pairs_emit_kernel(const PoolRec *__restrict__ kept, const PoolCtrl *ctrl, int32_t *pairs_out, int32_t cap,
+                       int32_t *n_pairs_out) {
+    const int m = int(ctrl->n_kept[0]);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const PoolRec me = kept[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) {
+            const PoolRec o = kept[j];
+            rank += (o.cost < me.cost) || (o.cost == me.cost && o.rank < me.rank);
+        }
+        if (rank < cap) {
+            int p[4], plan;
+            split_rank(me.rank, p, plan);
+            int32_t *row = pairs_out + size_t(rank) * 4;
+            row[0] = p[0]; row[1] = p[1]; row[2] = plan; row[3] = me.cost;
+        }
+    }
+    if (threadIdx.x == 0) *n_pairs_out = m;
+}
+
 struct PoolWorkspace {
     int4 *cust; int32_t *list, *slack, *cnt; unsigned int *item_off; PoolRec *recs[2]; PoolRec *act[2]; PoolRec *kept;
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolCtrl *ctrl; size_t bytes;
@@ -1135,6 +1203,47 @@ extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, i
     if (n_shards < 1 || shard < 0 || shard >= n_shards) return TD_ERR_INVALID;
     return td_pool_find_shards(demand, n, dist, n_stands, pool_size, shard, 1, n_shards, plans_out, cap, n_plans_out, stats,
                                workspace, workspace_bytes, max_feasible, stream);
+}
+
+extern "C" size_t td_pool_pairs_workspace_bytes(int n) {
+    if (n < 0) return 0;
+    return td::carve_pool(nullptr, n, 1, 1, int64_t(n) * n + 16).bytes;
+}
+
+extern "C" int td_pool_pairs(const int32_t *from, const int32_t *to, int n, const int32_t *dist, int n_stands,
+                             int accept_all, double max_loss, int32_t *pairs_out, int32_t cap, int32_t *n_pairs_out,
+                             void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace td;
+    if (n < 0 || n > TD_POOL_MAX_CUSTOMERS || n_stands <= 0 || cap < 0 || !n_pairs_out) return TD_ERR_INVALID;
+    if (!have_device()) return TD_ERR_NO_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n < 2) { TD_CUDA_TRY(cudaMemsetAsync(n_pairs_out, 0, sizeof(int32_t), st)); return TD_OK; }
+    if (!from || !to || !dist || !workspace || (cap > 0 && !pairs_out)) return TD_ERR_INVALID;
+    if (workspace_bytes < td_pool_pairs_workspace_bytes(n)) return TD_ERR_WORKSPACE;
+    const int64_t recs = int64_t(n) * n + 16;
+    PoolWorkspace w = carve_pool(workspace, n, 1, 1, recs);
+    TD_CUDA_TRY(cudaMemsetAsync(w.ctrl, 0, sizeof(PoolCtrl), st));
+    const int sms = device_sm_count();
+    pool_pairs_enum_kernel<<<sms * 8, 256, 0, st>>>(from, to, n, dist, n_stands, accept_all, max_loss, w.recs[0], w.ctrl);
+    TD_LAUNCH_CHECK();
+    SelArgs sa;
+    sa.list[0] = w.recs[0]; sa.list[1] = w.recs[1]; sa.act[0] = w.act[0]; sa.act[1] = w.act[1]; sa.ctrl = w.ctrl;
+    sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
+    sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = 2;
+    sa.n_slots = 1; sa.step = n + 1; sa.shard_begin = 0; sa.keep_cap = n / 2 + 1; sa.first_pass = 1; sa.cost_hi = INT_MAX;
+    int per_sm = 0;
+    TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_select_kernel, kSelThreads, 0));
+    if (per_sm < 1) return TD_ERR_CUDA;
+    per_sm = per_sm > 4 ? 4 : per_sm;
+    void *sargs[] = {(void *)&sa};
+    {
+        ProfScope prof(TD_PROF_POOL_SELECT, st);
+        TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)pool_select_kernel, dim3(sms * per_sm), dim3(kSelThreads), sargs, 0, st));
+    }
+    count_launch();
+    pool_pairs_emit_kernel<<<1, 1024, 0, st>>>(w.kept, w.ctrl, pairs_out, cap, n_pairs_out);
+    TD_LAUNCH_CHECK();
+    return TD_OK;
 }
 
 namespace td {

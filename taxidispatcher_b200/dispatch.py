@@ -28,7 +28,7 @@ from ._lib import BIG_COST, INT32_MAX, POOL_REC_W, AssignStats, LcmParams, PoolS
 
 __all__ = ["BIG_COST", "Engine", "calculate_cost", "solve", "solve_dispatch", "solve_full", "LCM", "LCM_heuristic",
            "LCM_split", "LCM_greedy_opt", "LCM_simulate", "LCM_java", "find_pool", "find_pool_all", "find_pool_block",
-           "pool_merge",
+           "find_pool_pairs", "pool_merge",
            "TaxiDispatchError"]
 
 
@@ -185,6 +185,20 @@ class Engine:
             check(rc, "td_pool_find_shards")
             return out, cnt, (list(st) if want_stats else None)
         raise TaxiDispatchError(_lib.TD_ERR_CAPACITY, "td_pool_find_shards")
+
+    def pool_pairs(self, frm: torch.Tensor, to: torch.Tensor, dist: torch.Tensor, accept_all: bool = True,
+                   max_loss: float = 1.01):
+        """Simulator.findPool: returns (pairs [cap,4] = custA, custB, plan, cost; count) device tensors."""
+        n = int(frm.numel())
+        cap = n // 2 + 1
+        out = torch.empty((cap, 4), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nbytes = self.lib.td_pool_pairs_workspace_bytes(n)
+        ws = self._workspace(("pairs", n), nbytes)
+        rc = self.lib.td_pool_pairs(_ptr(frm), _ptr(to), n, _ptr(dist), int(dist.shape[0]), 1 if accept_all else 0,
+                                    float(max_loss), _ptr(out), cap, _ptr(cnt), _ptr(ws), ws.numel(), _stream())
+        check(rc, "td_pool_pairs")
+        return out, cnt
 
     def pool_merge(self, shard_plans: torch.Tensor, total: int, n: int, pool_size: int):
         out = torch.empty((max(total, 1), POOL_REC_W), dtype=torch.int32, device=self.device)
@@ -343,6 +357,17 @@ def find_pool_block(demand, dist, pool_size: int, shard_begin: int, shard_count:
     return [(plans[s, : int(counts[s])].copy(),
              {"evaluated": st[s].evaluated, "feasible": st[s].feasible, "kept": st[s].kept, "rounds": st[s].rounds,
               "passes": st[s].passes}) for s in range(shard_count)]
+
+
+def find_pool_pairs(frm, to, dist, accept_all: bool = True, max_loss: float = 1.01):
+    """Simulator.findPool (Simulator.java:681-758): list of (custA, custB, plan, cost) in scan order;
+    custA / custB are positions in the given arrays; from < 0 marks a removed row."""
+    n = len(frm)
+    if n < 2:
+        return np.zeros((0, 4), np.int32)
+    eng = engine()
+    out, cnt = eng.pool_pairs(_h2d_i32(frm), _h2d_i32(to), _h2d_i32(dist), accept_all, max_loss)
+    return out[: int(cnt.item())].cpu().numpy()
 
 
 def pool_merge(shard_plans, n: int, pool_size: int):

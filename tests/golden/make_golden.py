@@ -59,7 +59,15 @@ def pool_case(dem, k, label):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-722", action="store_true")
+    ap.add_argument("--only-large", type=int, default=0, help="only write pool<N>.json for N customers (minutes of CPU)")
     a = ap.parse_args()
+    if a.only_large:
+        dem = g.pool_demand(a.only_large, seed=a.only_large)
+        c = pool_case(dem, 4, "large_%d" % a.only_large)
+        c["n_stands"] = 50
+        c["seed"] = a.only_large
+        dump("pool%d.json" % a.only_large, c)
+        return
     assert pool_ref.reference_binary(), "build oracle/_ref first: make -C oracle ref"
 
     # ---- pool: small cases (KAT P1) with the inputs inlined ---------------------------------
