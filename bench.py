@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--components", default="all", choices=["all", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool-large", type=int, default=5000, help="customers of the north-star pool component (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
 
@@ -356,6 +357,14 @@ def main():
            "api": "taxidispatcher_b200.find_pool_all(demand, dist, 4)" if world == 1 else
                   "taxidispatcher_b200.parallel.find_pool_sharded(demand, dist, 4)"}
 
+    # ---- north-star scale: 4-passenger pool over 5000 customers, sharded like the 722 job -----------
+    pool_large = None
+    if args.components == "all" and args.pool_large > 0:
+        try:
+            pool_large = run_pool_large(torch, dist, np, g, eng, parallel, args.pool_large, rank, world, hbm_peak)
+        except Exception as e:
+            pool_large = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- CPU baseline + the other kernels (rank 0, N = 1 only) -----------------------------------
     cpu_baseline = None
     components = {}
@@ -373,6 +382,12 @@ def main():
                 components = run_components(torch, np, g, eng, lib, _lib, dispatch, hbm_peak, flush_l2)
             except Exception as e:
                 components = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:
+                components["simulator_replay"] = run_simulator_component()
+            except Exception as e:
+                components["simulator_replay"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if pool_large is not None:
+        components["pool_%d" % args.pool_large] = pool_large
 
     if world > 1:
         dist.barrier()
@@ -391,6 +406,109 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_pool_large(torch, dist, np, g, eng, parallel, n_cust, rank, world, hbm_peak):
+    """north_star: 4-passenger pool over >= 5k waiting customers.  The feasible set (~4e10 plans at 5000
+    customers) does not fit in memory, so td_pool_find_shards runs its cost-window passes (SURVEY 'hard parts':
+    pool result capacity).  Each rank takes its contiguous block of the 8 logical shards; plans/s = all leaf
+    plans of the job / max-over-ranks device time.  Checked through size-independent properties."""
+    dem_np = g.pool_demand(n_cust, seed=n_cust)
+    dist_np = g.stand_distances(POOL_STANDS)
+    dev = eng.device
+    dem_d, dist_d = torch.from_numpy(dem_np).to(dev), torch.from_numpy(dist_np).to(dev)
+    mine = parallel.shards_for_rank(rank, world)
+    slots = (8 + world - 1) // world
+    cap = n_cust // 2 + 1
+    slot_plans = torch.zeros((slots, cap, 9), dtype=torch.int32, device=dev)
+    slot_counts = torch.zeros(slots, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st = []
+    if mine:
+        _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, mine[0], len(mine), 8, max_feasible=200_000_000,
+                                        out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)])
+    if world > 1:
+        allp = torch.zeros((world * slots, cap, 9), dtype=torch.int32, device=dev)
+        allc = torch.zeros(world * slots, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allp, slot_plans)
+        dist.all_gather_into_tensor(allc, slot_counts)
+    else:
+        allp, allc = slot_plans, slot_counts
+    sl = []
+    for r in range(world):
+        sh_r = parallel.shards_for_rank(r, world)
+        sl += sh_r + [0] * (slots - len(sh_r))
+    merged, mcnt = eng.pool_merge_padded(allp, allc, torch.tensor(sl, dtype=torch.int32, device=dev), n_cust, POOL_K)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([sum(int(s.evaluated) for s in st), sum(int(s.feasible) for s in st)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    sec = float(ms.item()) * 1e-3
+    ev, fe = int(tot[0]), int(tot[1])
+    # properties (rank 0): merged plans are customer-disjoint, sorted by cost, each one feasible under the
+    # reference's wait and detour rules (formulas of SURVEY 8(a)), and every shard's survivors lead in their shard
+    m = merged[: int(mcnt.item())].cpu().numpy()
+    ok = True
+    if rank == 0 and len(m):
+        F, T, W, L = (dem_np[:, k].astype(np.int64) for k in (1, 2, 3, 4))
+        p, q, cost = m[:, :4], m[:, 4:8], m[:, 8]
+        ok = ok and bool((np.diff(cost) >= 0).all()) and len(set(p.ravel().tolist())) == p.size
+        legs = dist_np[F[p[:, :-1]], F[p[:, 1:]]]
+        cum = np.concatenate([np.zeros((len(p), 1), np.int64), np.cumsum(legs, 1)], 1)
+        first = dist_np[F[p[:, -1]], T[q[:, 0]]]
+        drops = dist_np[T[q[:, :-1]], T[q[:, 1:]]]
+        ok = ok and bool((cum <= W[p]).all()) and bool((legs.sum(1) + first + drops.sum(1) == cost).all())
+        dcum = np.concatenate([np.zeros((len(p), 1), np.int64), np.cumsum(drops, 1)], 1) + first[:, None]
+        for d in range(4):
+            c = q[:, d]
+            pos = (p == c[:, None]).argmax(1)
+            suffix = np.array([legs[i, pos[i]:].sum() for i in range(len(p))])
+            ok = ok and bool((suffix + dcum[:, d] <= dist_np[F[c], T[c]] * (1 + L[c] / 100.0)).all())
+    per_gpu = ev / sec / world
+    return {"customers": n_cust, "seconds": sec, "plans_evaluated": ev, "feasible": fe, "merged_plans": int(len(m)),
+            "plans_per_s": ev / sec, "enumeration_passes": int(st[0].passes) if st else None, "properties_ok": bool(ok),
+            "roofline": {"bound": "hbm", "achieved": per_gpu * LOGICAL_B_PER_PLAN / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": per_gpu * LOGICAL_B_PER_PLAN / 1e9 / hbm_peak,
+                         "bytes_model": "logical 80 B per evaluated plan, per GPU, whole call (all passes, selection, merge)"}}
+
+
+def run_simulator_component():
+    """Config 4: replay of simulations/taxi_demand.txt (120 one-minute dispatch batches, 42 161 customers)."""
+    import gzip
+    from taxidispatcher_b200 import formats
+    from taxidispatcher_b200.simulator import Simulator
+    rows = formats.read_taxi_demand(gzip.open(os.path.join(ROOT, "tests", "golden", "taxi_demand.txt.gz"), "rt").read())
+    gold = [ln for ln in open(os.path.join(ROOT, "tests", "golden", "simulog_solv.txt")).read().split("\n") if ln.startswith("t:")]
+    sim = Simulator(rows)
+    t0 = time.perf_counter()
+    log, met = sim.run(120)
+    sec = time.perf_counter() - t0
+    match = 0
+    for a, b in zip(log, gold):
+        if a != b:
+            break
+        match += 1
+    out = {"seconds_120_steps": sec, "kernel_seconds": {k: round(v, 4) for k, v in sim.backend.times.items()},
+           "golden_log_lines_identical": match, "reference_seconds": 2603,
+           "metrics": {k: met[k] for k in ("Total dropped customers", "Total pickedup customers", "Max model size",
+                                           "Max solver size", "Max POOL size", "Total second customers in POOL")}}
+    try:
+        from oracle.sim_backend import OracleBackend
+        ref = Simulator(rows, backend=OracleBackend())
+        t0 = time.perf_counter()
+        ref.run(120)
+        out["cpu_oracle_seconds"] = time.perf_counter() - t0
+        out["cpu_oracle_kernel_seconds"] = {k: round(v, 3) for k, v in ref.backend.times.items()}
+    except Exception as e:
+        out["cpu_oracle_seconds"] = "failed: %s" % e
+    return out
 
 
 def run_components(torch, np, g, eng, lib, _lib, dispatch, hbm_peak, flush_l2):

@@ -80,7 +80,8 @@ def run_reference(demand, pool_size, shard, workdir=None):
         res = subprocess.run([exe, str(pool_size), str(shard), "demand.csv", str(len(dem)), "out.csv"],
                              cwd=td, capture_output=True, text=True, check=True)
         plans = parse_result_csv(open(os.path.join(td, "out.csv")).read(), pool_size)
-    m = {k: int(v) for k, v in re.findall(r"(Count ALL|Count|Not duplicated count): (\d+)", res.stdout)}
+    # count_all is a 32-bit `int` in the reference (pool_n.c:28) and wraps beyond 2^31 leaf plans per shard
+    m = {k: int(v) for k, v in re.findall(r"(Count ALL|Count|Not duplicated count): (-?\d+)", res.stdout)}
     stats = {"evaluated": m.get("Count ALL"), "feasible": m.get("Count"), "kept": m.get("Not duplicated count")}
     return plans, stats
 

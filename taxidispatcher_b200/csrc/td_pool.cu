@@ -222,10 +222,12 @@ __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, boo
         // abandon the rest of the current chunk (mark holes) and reserve a new one
         if (wo.base != 0xffffffffu)
             for (unsigned t = wo.used + lane; t < kChunk; t += 32) a.recs[wo.base + t].cost = -1;
-        unsigned nb = 0;
-        if (lane == 0) nb = atomicAdd(&a.ctrl->n_records, unsigned(kChunk));
+        unsigned nb = 0xffffffffu;
+        // once the list has overflowed nobody reserves any more (the counter must not run away and wrap)
+        if (lane == 0 && *reinterpret_cast<volatile unsigned *>(&a.ctrl->overflow) == 0)
+            nb = atomicAdd(&a.ctrl->n_records, unsigned(kChunk));
         nb = __shfl_sync(0xffffffffu, nb, 0);
-        if (nb + kChunk > a.cap) {
+        if ((unsigned long long)nb + kChunk > (unsigned long long)a.cap) {
             if (lane == 0) a.ctrl->overflow = 1;
             wo.base = 0xffffffffu; wo.used = kChunk;  // drop records from now on (counts stay exact)
             return;
@@ -1138,7 +1140,7 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
         int cost_hi = INT_MAX;
         const bool use_alive = !first_select;
         // big inputs: a 1/64 sampling pass estimates the histogram so that the full pass does not overflow
-        const bool sample = (long long)n_items_host > (1ll << 21);
+        const bool sample = (long long)n_items_host > (1ll << 18);
         if (sample) {
             TDH_RC_LOCAL(reset_pass());
             int rc = run_enum(cost_lo, INT_MAX, use_alive, false, 64);
