@@ -292,11 +292,16 @@ def main():
         for i in range(args.steps):
             flush_l2()
             ev0[i].record()
-            pool_step()
+            merged_last = pool_step()[:2]
             ev1[i].record()
         barrier()
     launches = int(lib.td_launch_count())
     lib.td_prof_enable(0)
+    # the timed steps ran asynchronously (no host round trip): make sure the last one was a complete, valid job
+    assert int(slot_counts[: len(my_shards)].min().item()) >= 0, "record list overflowed inside the timed region"
+    if rank == 0:
+        last = merged_last[0][: int(merged_last[1].item())].cpu().numpy()
+        assert last.tolist() == golden, "timed steps produced a different result than the golden merge"
     step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:

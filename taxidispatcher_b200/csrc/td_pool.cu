@@ -208,6 +208,7 @@ __device__ __forceinline__ int cand_count(const int32_t *cnt, int s, int w) {
 
 struct WarpOut {  // per-warp slice of the record list
     unsigned base, used;
+    bool dead;    // the list overflowed: this warp stops materialising (counters and histogram stay exact)
 };
 
 __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, bool has, unsigned long long rank, int cost,
@@ -216,7 +217,7 @@ __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, boo
     if (has) atomicAdd(&whist[cost < 0 ? 0 : (cost < kBuckets ? cost : kBuckets - 1)], 1u);
     has = has && cost < a.cost_hi && a.item_stride == 1;
     const unsigned ball = __ballot_sync(0xffffffffu, has);
-    if (ball == 0) return;
+    if (ball == 0 || wo.dead) return;
     const unsigned need = __popc(ball);
     if (wo.used + need > kChunk) {
         // abandon the rest of the current chunk (mark holes) and reserve a new one
@@ -229,7 +230,7 @@ __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, boo
         nb = __shfl_sync(0xffffffffu, nb, 0);
         if ((unsigned long long)nb + kChunk > (unsigned long long)a.cap) {
             if (lane == 0) a.ctrl->overflow = 1;
-            wo.base = 0xffffffffu; wo.used = kChunk;  // drop records from now on (counts stay exact)
+            wo.base = 0xffffffffu; wo.used = kChunk; wo.dead = true;
             return;
         }
         wo.base = nb; wo.used = 0;
@@ -315,7 +316,7 @@ pool_enum_kernel(EnumArgs a) {
     const int n_lead = a.stop - a.start;
     unsigned long long my_eval = 0, my_feas = 0;
     int cur_slot = -1;
-    WarpOut wo{0xffffffffu, unsigned(kChunk)};
+    WarpOut wo{0xffffffffu, unsigned(kChunk), false};
     __shared__ unsigned s_hist[kEnumThreads / 32][kBuckets];   // per-warp cost histogram of the warp's current shard
     unsigned *whist = s_hist[threadIdx.x >> 5];
     for (int b = lane; b < kBuckets; b += 32) whist[b] = 0;

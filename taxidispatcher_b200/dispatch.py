@@ -183,6 +183,12 @@ class Engine:
                     self._ws[key] = mf
                     continue
             check(rc, "td_pool_find_shards")
+            if want_stats and max_feasible is None and st[0].passes > 1:
+                # the feasible set did not fit the record list in one pass: remember a capacity that does (bounded
+                # by ~4 GiB per list) so that later calls -- in particular asynchronous ones, which cannot fall back
+                # to cost windows -- run single-pass
+                need = sum(int(s.feasible) for s in st) + 1024
+                self._ws[key] = max(mf, min(need, 1 << 28))
             return out, cnt, (list(st) if want_stats else None)
         raise TaxiDispatchError(_lib.TD_ERR_CAPACITY, "td_pool_find_shards")
 
