@@ -34,6 +34,8 @@
 // reports rows_scanned so achieved GB/s = 4 n rows_scanned / time.
 #include "td_common.cuh"
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -52,6 +54,10 @@ struct AsgCtrl {
     unsigned int free_after_init;
     unsigned int phases, levels, augment, pad;
     unsigned long long rows_scanned;
+    unsigned long long stale_cells;   // cells re-read to refresh cached level-0 distances
+    long long sfree;                  // sum of the phase lengths D: every still-free row has u = u_init + sfree
+    unsigned int nstale, pad3;
+    unsigned long long t_prof[8];     // ns spent by CTA 0 in: scan, sync, settle, sync, phase start, augment (diagnostics)
     long long objective;
     int status;
     int pad2;
@@ -59,7 +65,9 @@ struct AsgCtrl {
 
 struct AsgArgs {
     const int32_t *cost; int n;
-    long long *u, *v, *drow;
+    long long *u, *v, *drow, *uinit, *vinit;
+    unsigned long long *base0;        // per column: min over the FREE rows of (c - u_init - v_init), packed with the row
+    int32_t *stale;
     int32_t *vmin; int32_t *mate_r, *mate_c, *root, *claim, *prop, *argcol;
     unsigned long long *distpred; uint8_t *settled;
     int32_t *frontier[2]; int32_t *sinks;
@@ -222,6 +230,15 @@ assign_kernel(AsgArgs a) {
     const int gwarp = tid >> 5, nwarps = nthreads >> 5;
     __shared__ unsigned long long s_red[kAsgThreads / 32];
     AsgCtrl *ctrl = a.ctrl;
+    unsigned long long t_last = 0;
+    auto tick = [&](int k) {   // thread 0 only: accumulate wall time since the previous tick into bucket k
+        if (tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (k >= 0) ctrl->t_prof[k] += t - t_last;
+            t_last = t;
+        }
+    };
 
     // ================= init =====================================================================
     for (int j = tid; j < n; j += nthreads) { a.vmin[j] = INT_MAX; a.mate_c[j] = -1; a.prop[j] = INT_MAX; }
@@ -273,10 +290,12 @@ assign_kernel(AsgArgs a) {
         grid.sync();
     }
 
+    for (int i = tid; i < n; i += nthreads) { a.uinit[i] = a.u[i]; a.vinit[i] = a.v[i]; }
     // ================= phases ===================================================================
     bool first_phase = true;
     for (int phase = 0;; ++phase) {
         // ---- P0: reset search state, frontier = all free rows ---------------------------------
+        tick(-1);
         for (int j = tid; j < n; j += nthreads) { a.distpred[j] = kDistInf; a.settled[j] = 0; }
         for (int base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
             const int i = base + threadIdx.x;
@@ -299,13 +318,49 @@ assign_kernel(AsgArgs a) {
         first_phase = false;
         if (nfree == 0) break;
         if (phase >= a.max_phases) { if (tid == 0) ctrl->status = TD_ERR_NOT_CONVERGED; break; }
+        if (phase > 0) {
+            // Level 0 without re-reading the free rows.  Every free row has been free since the start and has
+            // received the same potential shift (sfree), and rows only LEAVE the free set, so the column minimum
+            // over the free rows taken once (base0) stays valid until its arg-min row is matched; only those
+            // columns are refreshed (a strided read of the column over the free-row list).
+            for (int j = tid; j < n; j += nthreads)
+                if (a.mate_r[dp_row(a.base0[j])] >= 0) a.stale[atomicAdd(&ctrl->nstale, 1u)] = j;
+            grid.sync();
+            const unsigned ns_cols = ctrl->nstale;
+            for (unsigned sidx = gwarp; sidx < ns_cols; sidx += nwarps) {
+                const int j = a.stale[sidx];
+                const long long vj0 = a.vinit[j];
+                unsigned long long best = kDistInf;
+                for (unsigned t = lane; t < nfree; t += 32) {
+                    const int i = a.frontier[0][t];
+                    const unsigned long long key = pack_dp((long long)__ldg(a.cost + size_t(i) * n + j) - a.uinit[i] - vj0, i);
+                    best = key < best ? key : best;
+                }
+                best = warp_min_u64(best);
+                if (lane == 0) a.base0[j] = best;
+            }
+            if (tid == 0) ctrl->stale_cells += (unsigned long long)ns_cols * nfree;
+            grid.sync();
+            const long long sfree = ctrl->sfree;
+            unsigned long long lmin = kDistInf;
+            for (int j = tid; j < n; j += nthreads) {
+                const unsigned long long b = a.base0[j];
+                const long long d0 = dp_dist(b) + a.vinit[j] - a.v[j] - sfree;
+                a.distpred[j] = pack_dp(d0, dp_row(b));
+                lmin = (unsigned long long)d0 < lmin ? (unsigned long long)d0 : lmin;
+            }
+            lmin = warp_min_u64(lmin);
+            if (lane == 0 && lmin != kDistInf) atomicMin(&ctrl->gmin[0], lmin);
+            if (tid == 0) ctrl->nstale = 0;
+        }
 
         int cur = 0;
         long long dstar = 0;
+        tick(4);
         for (int level = 0;; ++level) {
             const int slot = level % 3;
             // ---- (a) relax: every frontier row against all unsettled columns ------------------
-            const unsigned fc = ctrl->fcount[cur];
+            const unsigned fc = (phase > 0 && level == 0) ? 0u : ctrl->fcount[cur];   // level 0 comes from the cache
             unsigned long long bmin = kDistInf;
             sweep_rows<1, kVec>(a, a.frontier[cur], int(fc), gwarp, nwarps, lane, bmin);
             bmin = warp_min_u64(bmin);
@@ -317,7 +372,9 @@ assign_kernel(AsgArgs a) {
                 if (threadIdx.x == 0 && m != kDistInf) atomicMin(&ctrl->gmin[slot], m >> kRowBits);
             }
             if (tid == 0) ctrl->rows_scanned += fc;
+            tick(0);
             grid.sync();
+            tick(1);
             // ---- (b) settle every column at the new minimum distance -------------------------
             const unsigned long long dl = ctrl->gmin[slot];
             if (dl == kDistInf) { if (tid == 0) ctrl->status = TD_ERR_NOT_CONVERGED; dstar = -1; break; }
@@ -327,6 +384,7 @@ assign_kernel(AsgArgs a) {
                 const int j = base + threadIdx.x;
                 bool push = false;
                 int mate = -1;
+                if (phase == 0 && level == 0 && j < n) a.base0[j] = a.distpred[j];   // sfree = 0, v = v_init here
                 if (j < n && !a.settled[j]) {
                     const unsigned long long k = a.distpred[j];
                     if (k != kDistInf) {
@@ -355,7 +413,9 @@ assign_kernel(AsgArgs a) {
             carry = warp_min_u64(carry);
             if (lane == 0 && carry != kDistInf) atomicMin(&ctrl->gmin[(level + 1) % 3], carry);
             if (tid == 0) { ctrl->gmin[(level + 2) % 3] = kDistInf; ctrl->levels += 1; }
+            tick(2);
             grid.sync();
+            tick(3);
             if (tid == 0) ctrl->fcount[cur] = 0;  // consumed; becomes the target two levels from now
             if (ctrl->nsinks > 0) { dstar = delta; break; }
             cur ^= 1;
@@ -390,10 +450,11 @@ assign_kernel(AsgArgs a) {
         for (int j = tid; j < n; j += nthreads)
             if (a.settled[j]) a.v[j] -= dstar - dp_dist(a.distpred[j]);
         if (tid == 0) {
-            ctrl->nsinks = 0; ctrl->fcount[0] = ctrl->fcount[1] = 0; ctrl->phases += 1;
+            ctrl->nsinks = 0; ctrl->fcount[0] = ctrl->fcount[1] = 0; ctrl->phases += 1; ctrl->sfree += dstar;
             ctrl->gmin[0] = ctrl->gmin[1] = ctrl->gmin[2] = kDistInf;
         }
         grid.sync();
+        tick(5);
     }
 
     // ================= finish ===================================================================
@@ -420,6 +481,8 @@ static AsgArgs carve_assign(void *ws, int n, size_t *bytes) {
     const size_t nn = n > 0 ? n : 1;
     a.ctrl = c.take<AsgCtrl>(1);
     a.u = c.take<long long>(nn); a.v = c.take<long long>(nn); a.drow = c.take<long long>(nn);
+    a.uinit = c.take<long long>(nn); a.vinit = c.take<long long>(nn);
+    a.base0 = c.take<unsigned long long>(nn); a.stale = c.take<int32_t>(nn);
     a.distpred = c.take<unsigned long long>(nn);
     a.vmin = c.take<int32_t>(nn); a.mate_r = c.take<int32_t>(nn); a.mate_c = c.take<int32_t>(nn);
     a.root = c.take<int32_t>(nn); a.claim = c.take<int32_t>(nn); a.prop = c.take<int32_t>(nn); a.argcol = c.take<int32_t>(nn);
@@ -479,12 +542,16 @@ extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_o
         TD_CUDA_TRY(cudaMemcpyAsync(&h, a.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
         TD_CUDA_TRY(cudaStreamSynchronize(st));
         stats->objective = h.objective;
-        stats->rows_scanned = int64_t(h.rows_scanned) + 2 * int64_t(n);  // + the two init sweeps
+        // + the two init sweeps + the strided refreshes of cached level-0 minima (one cost cell each)
+        stats->rows_scanned = int64_t(h.rows_scanned) + 2 * int64_t(n) + int64_t(h.stale_cells / (unsigned long long)n);
         stats->auction_rounds = kGreedyRounds;
         stats->phases = int32_t(h.phases);
         stats->search_steps = int32_t(h.levels);
         stats->augmentations = int32_t(h.augment);
         stats->unassigned_after_auction = int32_t(h.free_after_init);
+        if (getenv("TD_ASSIGN_PROF"))
+            fprintf(stderr, "[td_assign] us: scan %.0f sync1 %.0f settle %.0f sync2 %.0f phase_start %.0f augment %.0f\n",
+                    h.t_prof[0] / 1e3, h.t_prof[1] / 1e3, h.t_prof[2] / 1e3, h.t_prof[3] / 1e3, h.t_prof[4] / 1e3, h.t_prof[5] / 1e3);
         if (h.status != TD_OK) return h.status;
     }
     return TD_OK;
