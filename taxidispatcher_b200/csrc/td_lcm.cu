@@ -56,19 +56,48 @@ __global__ void lcm_transpose_kernel(const int32_t *__restrict__ in, int32_t *__
     }
 }
 
-// min key over the still-free entries of one contiguous line (a row of cost or of cost^T)
+// min key over the still-free entries of one contiguous line (a row of cost or of cost^T).
+// The rounds are latency-bound (a line is 8 KB at n = 2000 and comes from L2), so the scan keeps as many
+// loads in flight as it can: 4 x 16-byte cost loads + 4 x 4-byte flag loads per lane per trip when the
+// line is 16-byte aligned (n % 4 == 0), 4 scalar loads per trip otherwise.
 template <bool kIsRow>
 __device__ __forceinline__ uint64_t scan_line(const int32_t *__restrict__ line, int n, int fixed,
-                                              const uint8_t *other_free, int lane) {
+                                              const uint8_t *other_free, int lane, bool vec) {
     uint64_t best = kKeyInf;
+    auto key_of = [&](int32_t v, int t) -> uint64_t {
+        return pack_key(v, kIsRow ? uint32_t(fixed) * n + t : uint32_t(t) * n + fixed);
+    };
+    if (vec) {
+        const int nq = n >> 2;   // int4 groups
+        for (int g0 = lane; g0 < nq; g0 += 128) {
+            int4 c[4];
+            uchar4 f[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int gq = g0 + 32 * u;
+                if (gq < nq) {
+                    c[u] = *reinterpret_cast<const int4 *>(line + 4 * gq);
+                    f[u] = *reinterpret_cast<const uchar4 *>(other_free + 4 * gq);
+                } else {
+                    f[u] = make_uchar4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = 4 * (g0 + 32 * u);
+                if (f[u].x) { const uint64_t k = key_of(c[u].x, t); best = k < best ? k : best; }
+                if (f[u].y) { const uint64_t k = key_of(c[u].y, t + 1); best = k < best ? k : best; }
+                if (f[u].z) { const uint64_t k = key_of(c[u].z, t + 2); best = k < best ? k : best; }
+                if (f[u].w) { const uint64_t k = key_of(c[u].w, t + 3); best = k < best ? k : best; }
+            }
+        }
+        return warp_min_u64(best);
+    }
     int t = lane;
     for (; t + 96 < n; t += 128) {  // 4 independent loads in flight per lane
         int32_t v0 = line[t], v1 = line[t + 32], v2 = line[t + 64], v3 = line[t + 96];
         uint8_t f0 = other_free[t], f1 = other_free[t + 32], f2 = other_free[t + 64], f3 = other_free[t + 96];
-        uint64_t k0 = pack_key(v0, kIsRow ? uint32_t(fixed) * n + t : uint32_t(t) * n + fixed);
-        uint64_t k1 = pack_key(v1, kIsRow ? uint32_t(fixed) * n + t + 32 : uint32_t(t + 32) * n + fixed);
-        uint64_t k2 = pack_key(v2, kIsRow ? uint32_t(fixed) * n + t + 64 : uint32_t(t + 64) * n + fixed);
-        uint64_t k3 = pack_key(v3, kIsRow ? uint32_t(fixed) * n + t + 96 : uint32_t(t + 96) * n + fixed);
+        uint64_t k0 = key_of(v0, t), k1 = key_of(v1, t + 32), k2 = key_of(v2, t + 64), k3 = key_of(v3, t + 96);
         if (f0 && k0 < best) best = k0;
         if (f1 && k1 < best) best = k1;
         if (f2 && k2 < best) best = k2;
@@ -76,7 +105,7 @@ __device__ __forceinline__ uint64_t scan_line(const int32_t *__restrict__ line, 
     }
     for (; t < n; t += 32) {
         if (other_free[t]) {
-            uint64_t k = pack_key(line[t], kIsRow ? uint32_t(fixed) * n + t : uint32_t(t) * n + fixed);
+            uint64_t k = key_of(line[t], t);
             if (k < best) best = k;
         }
     }
@@ -84,7 +113,7 @@ __device__ __forceinline__ uint64_t scan_line(const int32_t *__restrict__ line, 
 }
 
 __global__ void __launch_bounds__(kLcmThreads)
-lcm_rounds_kernel(const int32_t *__restrict__ cost, const int32_t *__restrict__ costT, int n,
+lcm_rounds_kernel(const int32_t *__restrict__ cost, const int32_t *__restrict__ costT, int n, int vec,
                   td_lcm_params prm, unsigned long long *rowkey, unsigned long long *colkey,
                   uint8_t *rowfree, uint8_t *colfree, unsigned long long *picked, LcmCtrl *ctrl) {
     cg::grid_group grid = cg::this_grid();
@@ -104,11 +133,11 @@ lcm_rounds_kernel(const int32_t *__restrict__ cost, const int32_t *__restrict__ 
     grid.sync();
     for (int l = gwarp; l < 2 * n; l += nwarps) {
         if (l < n) {
-            uint64_t k = scan_line<true>(cost + size_t(l) * n, n, l, colfree, lane);
+            uint64_t k = scan_line<true>(cost + size_t(l) * n, n, l, colfree, lane, vec != 0);
             if (lane == 0) rowkey[l] = k;
         } else {
             int j = l - n;
-            uint64_t k = scan_line<false>(costT + size_t(j) * n, n, j, rowfree, lane);
+            uint64_t k = scan_line<false>(costT + size_t(j) * n, n, j, rowfree, lane, vec != 0);
             if (lane == 0) colkey[j] = k;
         }
     }
@@ -137,7 +166,7 @@ lcm_rounds_kernel(const int32_t *__restrict__ cost, const int32_t *__restrict__ 
                 if (!rowfree[l]) continue;
                 unsigned long long k = rowkey[l];
                 if (k != kKeyInf && !colfree[key_index(k) - uint32_t(l) * n]) {
-                    k = scan_line<true>(cost + size_t(l) * n, n, l, colfree, lane);
+                    k = scan_line<true>(cost + size_t(l) * n, n, l, colfree, lane, vec != 0);
                     if (lane == 0) rowkey[l] = k;
                 }
                 if (k < wmin) wmin = k;
@@ -146,7 +175,7 @@ lcm_rounds_kernel(const int32_t *__restrict__ cost, const int32_t *__restrict__ 
                 if (!colfree[j]) continue;
                 unsigned long long k = colkey[j];
                 if (k != kKeyInf && !rowfree[(key_index(k) - uint32_t(j)) / uint32_t(n)]) {
-                    k = scan_line<false>(costT + size_t(j) * n, n, j, rowfree, lane);
+                    k = scan_line<false>(costT + size_t(j) * n, n, j, rowfree, lane, vec != 0);
                     if (lane == 0) colkey[j] = k;
                 }
             }
@@ -376,13 +405,16 @@ extern "C" int td_lcm(const int32_t *cost, int n, const td_lcm_params *params, i
     TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcm_rounds_kernel, kLcmThreads, 0));
     if (per_sm < 1) return TD_ERR_CUDA;
     per_sm = per_sm > 2 ? 2 : per_sm;
+    if (n <= 4096) per_sm = 1;   // small instances are barrier-latency bound: fewer CTAs make grid.sync cheaper
     int grid = device_sm_count() * per_sm;
     // no point in more warps than lines to scan (2n); keeps grid.sync cheap for small n
     int need = (2 * n * 32 + kLcmThreads - 1) / kLcmThreads;
     if (grid > need) grid = need < 1 ? 1 : need;
     td_lcm_params prm = *params;
     const int32_t *costT = w.costT;
-    void *args[] = {(void *)&cost, (void *)&costT, (void *)&n, (void *)&prm, (void *)&w.rowkey, (void *)&w.colkey,
+    // 16-byte loads need aligned lines: n % 4 == 0 and aligned bases (the flag arrays are 256-byte aligned slices)
+    int vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0) ? 1 : 0;
+    void *args[] = {(void *)&cost, (void *)&costT, (void *)&n, (void *)&vec, (void *)&prm, (void *)&w.rowkey, (void *)&w.colkey,
                     (void *)&w.rowfree, (void *)&w.colfree, (void *)&w.picked, (void *)&w.ctrl};
     {
         ProfScope prof(TD_PROF_LCM, st);
