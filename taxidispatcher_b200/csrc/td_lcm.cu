@@ -405,7 +405,6 @@ extern "C" int td_lcm(const int32_t *cost, int n, const td_lcm_params *params, i
     TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcm_rounds_kernel, kLcmThreads, 0));
     if (per_sm < 1) return TD_ERR_CUDA;
     per_sm = per_sm > 2 ? 2 : per_sm;
-    if (n <= 4096) per_sm = 1;   // small instances are barrier-latency bound: fewer CTAs make grid.sync cheaper
     int grid = device_sm_count() * per_sm;
     // no point in more warps than lines to scan (2n); keeps grid.sync cheap for small n
     int need = (2 * n * 32 + kLcmThreads - 1) / kLcmThreads;
