@@ -204,6 +204,101 @@ lcm_rounds_kernel(const int32_t *__restrict__ cost, const int32_t *__restrict__ 
     }
 }
 
+// Small / medium instances (the state fits in shared memory: 18 n bytes): every CTA keeps a FULL replica of
+// the cached minima and of the free flags.  The selection and the staleness test are then pure shared-memory
+// work that every CTA repeats identically (no communication), the rescans of the stale lines are split over
+// the CTAs, and ONE grid.sync per round publishes the refreshed minima, which every CTA then pulls into its
+// replica.  Half the barriers and none of the dependent global round trips of the generic kernel.
+__global__ void __launch_bounds__(kLcmThreads)
+lcm_rounds_smem_kernel(const int32_t *__restrict__ cost, const int32_t *__restrict__ costT, int n, int vec,
+                       td_lcm_params prm, unsigned long long *gkey /* 2n: rows then columns */,
+                       unsigned long long *picked, LcmCtrl *ctrl) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char lsm[];
+    unsigned long long *rk = reinterpret_cast<unsigned long long *>(lsm);          // row minima
+    unsigned long long *ck = rk + n;                                                // column minima
+    const int nf = (n + 15) & ~15;
+    uint8_t *rf = reinterpret_cast<uint8_t *>(ck + n);                              // row free flags
+    uint8_t *cf = rf + nf;                                                          // column free flags
+    int *mine = reinterpret_cast<int *>(cf + nf);                                   // stale lines this CTA rescans (<= 2n)
+    __shared__ int s_nmine;
+    __shared__ unsigned long long s_min[kLcmThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kLcmThreads / 32;
+    const int G = gridDim.x, b = blockIdx.x;
+    const bool v = vec != 0;
+
+    for (int i = tid; i < n; i += kLcmThreads) { rf[i] = 1; cf[i] = 1; }
+    if (b == 0 && tid == 0) { ctrl->n_picked = 0; ctrl->rounds = 0; ctrl->g_final = kKeyInf; }
+    __syncthreads();
+    // initial minima: line l belongs to CTA l % G
+    for (int l = b + G * warp; l < 2 * n; l += G * nw) {
+        const unsigned long long k = l < n ? scan_line<true>(cost + size_t(l) * n, n, l, cf, lane, v)
+                                           : scan_line<false>(costT + size_t(l - n) * n, n, l - n, rf, lane, v);
+        if (lane == 0) gkey[l] = k;
+    }
+    grid.sync();
+    for (int l = tid; l < 2 * n; l += kLcmThreads) { const unsigned long long k = __ldcg(gkey + l); if (l < n) rk[l] = k; else ck[l - n] = k; }
+    __syncthreads();
+
+    auto stale = [&](int l) -> bool {   // free line whose cached partner has been taken
+        if (l < n) { const unsigned long long k = rk[l]; return rf[l] && k != kKeyInf && !cf[key_index(k) - uint32_t(l) * n]; }
+        const int j = l - n;
+        const unsigned long long k = ck[j];
+        return cf[j] && k != kKeyInf && !rf[(key_index(k) - uint32_t(j)) / uint32_t(n)];
+    };
+    for (unsigned round = 0;; ++round) {
+        // ---- select (replicated): row i takes its cached cell iff it is also its column's minimum ----
+        for (int i = tid; i < n; i += kLcmThreads) {
+            if (!rf[i]) continue;
+            const unsigned long long k = rk[i];
+            if (k == kKeyInf) continue;
+            const int j = int(key_index(k) - uint32_t(i) * n);
+            if (ck[j] == k) {
+                rf[i] = 0; cf[j] = 0;
+                if (b == 0) picked[atomicAdd(&ctrl->n_picked, 1u)] = k;
+            }
+        }
+        if (tid == 0) s_nmine = 0;
+        __syncthreads();
+        // ---- stale lines: this CTA rescans those with l % G == b ----
+        for (int l = tid; l < 2 * n; l += kLcmThreads)
+            if (l % G == b && stale(l)) mine[atomicAdd(&s_nmine, 1)] = l;
+        __syncthreads();
+        const int nm = s_nmine;
+        for (int t = warp; t < nm; t += nw) {
+            const int l = mine[t];
+            const unsigned long long k = l < n ? scan_line<true>(cost + size_t(l) * n, n, l, cf, lane, v)
+                                               : scan_line<false>(costT + size_t(l - n) * n, n, l - n, rf, lane, v);
+            if (lane == 0) __stcg(gkey + l, k);
+        }
+        grid.sync();
+        // ---- pull the refreshed minima into the replica (the predicate still sees the old keys) ----
+        for (int l = tid; l < 2 * n; l += kLcmThreads)
+            if (stale(l)) { const unsigned long long k = __ldcg(gkey + l); if (l < n) rk[l] = k; else ck[l - n] = k; }
+        __syncthreads();
+        // ---- smallest free key (replicated) -> termination ----
+        unsigned long long m = kKeyInf;
+        for (int i = tid; i < n; i += kLcmThreads) if (rf[i] && rk[i] < m) m = rk[i];
+        m = warp_min_u64(m);
+        if (lane == 0) s_min[warp] = m;
+        __syncthreads();
+        unsigned long long g = s_min[0];
+        for (int w2 = 1; w2 < nw; ++w2) g = s_min[w2] < g ? s_min[w2] : g;
+        __syncthreads();
+        bool done = (g == kKeyInf);
+        if (!done) {
+            const int32_t val = key_value(g);
+            if (prm.stop_above != INT32_MAX && val > prm.stop_above) done = true;
+            if (prm.stop_at_value != INT32_MAX && val >= prm.stop_at_value) done = true;
+            if (val > prm.mask_value) done = true;  // a masked cell wins every later argmin
+        }
+        if (done) {
+            if (b == 0 && tid == 0) { ctrl->g_final = g; ctrl->rounds = round + 1; }
+            break;
+        }
+    }
+}
+
 // ascending key order by counting smaller keys (P <= n picks; keys are unique)
 __global__ void lcm_rank_sort_kernel(const unsigned long long *__restrict__ picked,
                                      unsigned long long *__restrict__ sorted, const LcmCtrl *ctrl) {
@@ -352,7 +447,7 @@ lcm_finalize_kernel(const unsigned long long *__restrict__ sorted, int n, td_lcm
 
 struct LcmWorkspace {
     int32_t *costT;
-    unsigned long long *rowkey, *colkey, *picked, *sorted;
+    unsigned long long *rowkey, *colkey, *picked, *sorted, *gkey2;
     uint8_t *rowfree, *colfree;
     LcmCtrl *ctrl;
     size_t bytes;
@@ -366,6 +461,7 @@ static LcmWorkspace carve_lcm(void *ws, int n) {
     w.colkey = c.take<unsigned long long>(n);
     w.picked = c.take<unsigned long long>(n);
     w.sorted = c.take<unsigned long long>(n);
+    w.gkey2 = c.take<unsigned long long>(size_t(2) * n);
     w.rowfree = c.take<uint8_t>(n);
     w.colfree = c.take<uint8_t>(n);
     w.ctrl = c.take<LcmCtrl>(1);
@@ -401,21 +497,33 @@ extern "C" int td_lcm(const int32_t *cost, int n, const td_lcm_params *params, i
     lcm_transpose_kernel<<<tg, tb, 0, st>>>(cost, w.costT, n);
     TD_LAUNCH_CHECK();
 
-    int per_sm = 0;
-    TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcm_rounds_kernel, kLcmThreads, 0));
-    if (per_sm < 1) return TD_ERR_CUDA;
-    per_sm = per_sm > 2 ? 2 : per_sm;
-    int grid = device_sm_count() * per_sm;
-    // no point in more warps than lines to scan (2n); keeps grid.sync cheap for small n
-    int need = (2 * n * 32 + kLcmThreads - 1) / kLcmThreads;
-    if (grid > need) grid = need < 1 ? 1 : need;
     td_lcm_params prm = *params;
     const int32_t *costT = w.costT;
-    // 16-byte loads need aligned lines: n % 4 == 0 and aligned bases (the flag arrays are 256-byte aligned slices)
+    // 16-byte loads need aligned lines: n % 4 == 0 and aligned bases (the flag arrays are 16-byte aligned)
     int vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0) ? 1 : 0;
-    void *args[] = {(void *)&cost, (void *)&costT, (void *)&n, (void *)&vec, (void *)&prm, (void *)&w.rowkey, (void *)&w.colkey,
-                    (void *)&w.rowfree, (void *)&w.colfree, (void *)&w.picked, (void *)&w.ctrl};
-    {
+    const size_t smem_need = size_t(n) * 16 + 2 * size_t((n + 15) & ~15) + size_t(2 * n) * 4 + 64;
+    if (smem_need <= 200 * 1024) {
+        // replicated-state kernel: one CTA per SM at most, never more CTAs than a quarter of the lines
+        TD_CUDA_TRY(cudaFuncSetAttribute(lcm_rounds_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(200 * 1024)));
+        int grid = device_sm_count();
+        const int cap_grid = (2 * n + 3) / 4;
+        if (grid > cap_grid) grid = cap_grid < 1 ? 1 : cap_grid;
+        unsigned long long *gkey = w.gkey2;
+        void *args[] = {(void *)&cost, (void *)&costT, (void *)&n, (void *)&vec, (void *)&prm, (void *)&gkey, (void *)&w.picked,
+                        (void *)&w.ctrl};
+        ProfScope prof(TD_PROF_LCM, st);
+        TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lcm_rounds_smem_kernel, dim3(grid), dim3(kLcmThreads), args, smem_need, st));
+    } else {
+        int per_sm = 0;
+        TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcm_rounds_kernel, kLcmThreads, 0));
+        if (per_sm < 1) return TD_ERR_CUDA;
+        per_sm = per_sm > 2 ? 2 : per_sm;
+        int grid = device_sm_count() * per_sm;
+        // no point in more warps than lines to scan (2n); keeps grid.sync cheap for small n
+        int need = (2 * n * 32 + kLcmThreads - 1) / kLcmThreads;
+        if (grid > need) grid = need < 1 ? 1 : need;
+        void *args[] = {(void *)&cost, (void *)&costT, (void *)&n, (void *)&vec, (void *)&prm, (void *)&w.rowkey, (void *)&w.colkey,
+                        (void *)&w.rowfree, (void *)&w.colfree, (void *)&w.picked, (void *)&w.ctrl};
         ProfScope prof(TD_PROF_LCM, st);
         TD_CUDA_TRY(cudaLaunchCooperativeKernel((void *)lcm_rounds_kernel, dim3(grid), dim3(kLcmThreads), args, 0, st));
     }
