@@ -359,3 +359,26 @@ def test_pool_multi_pass_cost_windows(td):
             ref, rst = pool_ref.find(case_dem, d51, k, sh)
             assert o[0, : int(c[0])].cpu().numpy().tolist() == ref.tolist(), (k, sh)
             assert (s2[0].evaluated, s2[0].feasible) == (rst["evaluated"], rst["feasible"])
+
+
+def test_pool_1200_customers_golden_single_pass_and_windows(td):
+    """1200 customers (2.5e10 leaf plans, 1.5e8 feasible): the compiled reference needed minutes per shard; its
+    32-bit count_all wraps (pool_n.c:28), so evaluated is compared modulo 2^32.  Run once with room for every
+    record and once with a record list 40x too small (cost windows + alive pruning)."""
+    import torch
+    gold = load_golden("pool1200.json")
+    dem = g.pool_demand(1200, seed=1200)
+    assert sha(dem) == gold["demand_sha256"]
+    eng = td.engine()
+    dd, ds = torch.from_numpy(dem).cuda(), torch.from_numpy(g.stand_distances(50)).cuda()
+    for mf in (200_000_000, 4_000_000):
+        out, cnt, st = eng.pool_find_shards(dd, ds, 4, 0, 8, 8, max_feasible=mf)
+        counts = cnt.cpu().numpy()
+        for s in range(8):
+            gs = gold["shards"][s]
+            assert out[s, : counts[s]].cpu().numpy().tolist() == gs["plans"], (mf, s)
+            assert st[s].feasible == gs["stats"]["feasible"] and st[s].kept == gs["stats"]["kept"]
+            assert (st[s].evaluated - gs["stats"]["evaluated"]) % (1 << 32) == 0
+        merged, mc = eng.pool_merge_padded(out, cnt, None, 1200, 4)
+        assert merged[: int(mc.item())].cpu().numpy().tolist() == gold["merged"]
+    assert st[0].passes > 1
