@@ -46,13 +46,29 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_PINNED = {}   # numel -> reusable pinned staging buffer (cudaHostAlloc per call costs more than small copies)
+
+
 def _h2d_i32(a, pinned: bool = True) -> torch.Tensor:
-    """Host array-like -> int32 CUDA tensor through pinned staging (asynchronous copy)."""
+    """Host array-like -> int32 CUDA tensor through pinned staging (asynchronous copy on the current stream).
+    Staging buffers are reused; the stream is synchronised before a buffer is overwritten again."""
     arr = np.ascontiguousarray(np.asarray(a, dtype=np.int32))
-    t = torch.from_numpy(arr)
-    if pinned and arr.size:
-        t = t.pin_memory()
-    return t.to("cuda", non_blocking=True)
+    if not pinned or arr.size == 0:
+        return torch.from_numpy(arr).to("cuda")
+    if arr.size > (1 << 22):                       # big matrices: one-off pinned copy
+        return torch.from_numpy(arr).pin_memory().to("cuda", non_blocking=True)
+    slot = _PINNED.get(arr.size)
+    if slot is None:
+        slot = {"buf": torch.empty(arr.size, dtype=torch.int32).pin_memory(), "ev": None}
+        _PINNED[arr.size] = slot
+    if slot["ev"] is not None:
+        slot["ev"].synchronize()                   # the previous copy out of this buffer has finished
+    slot["buf"].numpy()[:] = arr.reshape(-1)
+    t = slot["buf"].to("cuda", non_blocking=True).reshape(arr.shape)
+    ev = torch.cuda.Event()
+    ev.record()
+    slot["ev"] = ev
+    return t
 
 
 class Engine:
