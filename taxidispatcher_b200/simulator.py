@@ -3,7 +3,7 @@ the dispatch kernels -- per-minute batches of 2-passenger pool -> cost matrix ->
 larger than MAX_NON_LCM) -> exact solve, over simulations/taxi_demand.txt.
 
 Host logic only (state machine of cabs and customers); every dispatch primitive goes through a backend:
-the product default `CudaBackend` calls the CUDA engine; tests inject a CPU backend built from oracle/
+the product default `CudaBackend` calls the CUDA engine; tests inject a CPU backend built from the test-only CPU restatements
 to check this host logic against the reference's golden log (simulations/simulog_solv.txt, KAT S1).
 No JVM exists here, so this file is a restatement, cited line by line:
 
