@@ -122,12 +122,12 @@ def _run_ref_slice(args):
     return int(m.group(1)) if m else 0
 
 
-def reference_sample(n_slices=8):
-    """One bounded sample of config 3 on the host cores: slices 0..n_slices-1 of the 64-way shard rule
-    of the UNMODIFIED pool_n.c (oracle/_ref/pool_n_big64), one process per slice, all at once (the
-    way findpool.c:138-142 fans out).  Returns (plans, seconds, processes)."""
+def reference_sample(n_slices=8, ways=64):
+    """One bounded sample of config 3 on the host cores: slices 0..n_slices-1 of a `ways`-way shard rule of the
+    UNMODIFIED pool_n.c (oracle/_ref/pool_n_big64 or _big512), one process per slice, all at once (the way
+    findpool.c:138-142 fans out).  Returns (plans, seconds, processes)."""
     from oracle import gen_inputs as g
-    exe = os.path.join(ROOT, "oracle", "_ref", "pool_n_big64")
+    exe = os.path.join(ROOT, "oracle", "_ref", "pool_n_big%d" % ways)
     if not os.path.exists(exe):
         from oracle import _clib
         _clib.build_ref()
@@ -149,17 +149,26 @@ def reference_sample(n_slices=8):
 
 
 SAMPLE_TEXT = "leading customers 0..95 of 722 (slices 0-7 of a 64-way pool_n.c shard rule, one process per slice)"
+SAMPLE_TEXT_512 = "leading customers 0..%d of 722 (%d slices of a 512-way pool_n.c shard rule, one process per slice)"
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
     try:
+        # size the per-step sample so that the whole run stays within a few minutes: 8 x 1/64 of the job (~3 s
+        # on 8 cores) for short runs, 1/512 slices (~0.3 s each, one per core) for long ones
+        cores = os.cpu_count() or 1
+        if args.steps + args.warmup <= 40:
+            ways, n_slices, sample = 64, 8, SAMPLE_TEXT
+        else:
+            ways, n_slices = 512, max(1, min(cores, 16))
+            sample = SAMPLE_TEXT_512 % (2 * n_slices - 1, n_slices)
         for _ in range(args.warmup):
-            reference_sample()
+            reference_sample(n_slices, ways)
         t_tot, plans_tot, procs = 0.0, 0, 1
         for _ in range(args.steps):
-            plans, dt, procs = reference_sample()
+            plans, dt, procs = reference_sample(n_slices, ways)
             t_tot += dt
             plans_tot += plans
         val = plans_tot / t_tot
@@ -167,8 +176,8 @@ def run_reference_arm(args, rank):
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": "pool_n 4-passenger pool search, 722 customers (SURVEY 8(d) config 3)",
-                           "pool_size": POOL_K, "customers": POOL_N, "stands": POOL_STANDS, "sample": SAMPLE_TEXT},
-                "cpu_baseline": {"value": val, "unit": "plans/s", "cores": procs, "kind": "reference", "sample": SAMPLE_TEXT},
+                           "pool_size": POOL_K, "customers": POOL_N, "stands": POOL_STANDS, "sample": sample},
+                "cpu_baseline": {"value": val, "unit": "plans/s", "cores": procs, "kind": "reference", "sample": sample},
                 "e2e": {"value": val, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
     except Exception as e:  # the oracle always exists; report instead of crashing the driver
@@ -190,6 +199,7 @@ def main():
     ap.add_argument("--pool-large", type=int, default=5000, help="customers of the north-star pool component (0: skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    args.steps = max(args.steps, 1)
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

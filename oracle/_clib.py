@@ -28,7 +28,7 @@ def build_ref(force: bool = False, ref_dir: str = "/root/reference"):
     (the GPU box only has the prebuilt file that travelled with the snapshot).
     """
     out = os.path.join(_HERE, "_ref", "pool_n_big")
-    if os.path.exists(out) and os.path.exists(out + "64") and not force:
+    if os.path.exists(out) and os.path.exists(out + "64") and os.path.exists(out + "512") and not force:
         return out
     if not os.path.exists(os.path.join(ref_dir, "pool_n.c")):
         return out if os.path.exists(out) else None
