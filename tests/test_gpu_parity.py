@@ -382,3 +382,44 @@ def test_pool_1200_customers_golden_single_pass_and_windows(td):
         merged, mc = eng.pool_merge_padded(out, cnt, None, 1200, 4)
         assert merged[: int(mc.item())].cpu().numpy().tolist() == gold["merged"]
     assert st[0].passes > 1
+
+
+def test_pool_large_tables_take_the_global_memory_paths(td):
+    """> 128 stands (distance table not staged in shared memory) and > 6144 customers (customer records not
+    staged): the enumeration falls back to read-only global loads; results must not change."""
+    rng = np.random.default_rng(77)
+    S = 200
+    dist = g.stand_distances(S)
+    n = 260
+    fr = rng.integers(0, S, n)
+    to = (fr + rng.integers(1, 30, n)) % S
+    dem = np.stack([np.arange(n), fr, to, rng.integers(0, 25, n), rng.integers(0, 40, n)], axis=1).astype(np.int32)
+    for k in (2, 3, 4):
+        plans, st = td.find_pool(dem, dist, k, 1, 4)
+        oplans, ost = pool_ref.find(dem, dist, k, 1, 4)
+        assert {q: st[q] for q in ost} == ost and np.array_equal(plans, oplans), k
+    n = 6400                                              # 16-byte customer records exceed the 96 KB staging budget
+    fr = rng.integers(0, 50, n)
+    to = (fr + rng.integers(1, 20, n)) % 50
+    dem = np.stack([np.arange(n), fr, to, np.zeros(n, int), rng.integers(0, 3, n)], axis=1).astype(np.int32)
+    d50 = g.stand_distances(50)
+    plans, st = td.find_pool(dem, d50, 2, 5, 8)           # wait 0: partners share the pickup stand
+    oplans, ost = pool_ref.find(dem, d50, 2, 5, 8)
+    assert {q: st[q] for q in ost} == ost and np.array_equal(plans, oplans)
+
+
+def test_cost_matrix_large_stand_table_without_staging(td):
+    """a stand row that does not fit the double-buffered shared-memory stage (S > 12288) uses the direct path"""
+    import torch
+    rng = np.random.default_rng(3)
+    S = 13000
+    eng = td.engine()
+    dist = torch.randint(0, 1000, (S, S), dtype=torch.int32, device="cuda")
+    cab_to = torch.from_numpy(rng.integers(0, S, 37).astype(np.int32)).cuda()
+    cust_from = torch.from_numpy(rng.integers(0, S, 53).astype(np.int32)).cuda()
+    out = eng.cost_matrix(dist, cab_to, cust_from, fill=-7, cutoff=900).cpu().numpy()
+    d = dist.cpu().numpy()
+    ref = np.full((53, 53), -7, np.int32)
+    blk = d[cab_to.cpu().numpy()[:, None], cust_from.cpu().numpy()[None, :]]
+    ref[:37, :53] = np.where(blk < 900, blk, -7)
+    assert np.array_equal(out, ref)
