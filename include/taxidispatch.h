@@ -189,6 +189,13 @@ int td_pool_pairs(const int32_t *from, const int32_t *to, int n, const int32_t *
                   int32_t *pairs_out /* cap x 4 */, int32_t cap, int32_t *n_pairs_out /* 1 */,
                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* After an ASYNCHRONOUS td_pool_find / td_pool_find_shards call (stats == NULL) on `workspace`: waits for the
+ * stream and reads the per-shard counters back (one small copy).  *overflow_out != 0: the record list was too
+ * small for a single pass -- counts_out holds -1 and the call has to be repeated synchronously (stats != NULL),
+ * which falls back to cost windows. */
+int td_pool_read_stats(const void *workspace, int shard_count, td_pool_stats *stats /* host[shard_count] */,
+                       int *overflow_out /* host, may be NULL */, void *stream);
+
 /* findpool.c:83-108: concatenated shard survivors (shard order) -> sort on column 8 -> greedy
  * disjoint scan.  Reference quirk kept: for pool_size < 4 findpool.c sorts on a column it never
  * filled (findpool.c:34-35,70), so the scan runs in concatenation order. */

@@ -1200,6 +1200,28 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
     return over_cap ? TD_ERR_CAPACITY : TD_OK;
 }
 
+extern "C" int td_pool_read_stats(const void *workspace, int shard_count, td_pool_stats *stats, int *overflow_out,
+                                  void *stream) {
+    using namespace td;
+    if (!workspace || shard_count < 1 || shard_count > kMaxSlots || !stats) return TD_ERR_INVALID;
+    if (!have_device()) return TD_ERR_NO_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static thread_local PoolCtrl h;
+    const PoolCtrl *ctrl = Carver(const_cast<void *>(workspace)).take<PoolCtrl>(1);
+    const size_t head = offsetof(PoolCtrl, rounds) + sizeof(unsigned int);
+    TD_CUDA_TRY(cudaMemcpyAsync(&h, ctrl, head, cudaMemcpyDeviceToHost, st));
+    TD_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int s = 0; s < shard_count; ++s) {
+        stats[s].evaluated = int64_t(h.evaluated[s]);
+        stats[s].feasible = int64_t(h.feasible[s]);
+        stats[s].kept = h.n_kept[s];
+        stats[s].rounds = int32_t(h.total_rounds);
+        stats[s].passes = 1;
+    }
+    if (overflow_out) *overflow_out = h.overflow ? 1 : 0;
+    return TD_OK;
+}
+
 extern "C" int td_pool_find(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size, int shard,
                             int n_shards, int32_t *plans_out, int32_t cap, int32_t *n_plans_out, td_pool_stats *stats,
                             void *workspace, size_t workspace_bytes, int64_t max_feasible, void *stream) {

@@ -174,9 +174,11 @@ class Engine:
     def pool_find_shards(self, demand: torch.Tensor, dist: torch.Tensor, pool_size: int, shard_begin: int = 0,
                          shard_count: int = 8, n_shards: int = 8, max_feasible: Optional[int] = None,
                          out: Optional[torch.Tensor] = None, counts_out: Optional[torch.Tensor] = None,
-                         want_stats: bool = True):
+                         want_stats: bool = True, defer_stats: bool = False):
         """Consecutive logical shards in one call (one enumeration + one selection launch for all of them).
-        out: [shard_count, cap, 9]; counts_out: [shard_count] int32 (device).  Returns (out, counts, stats list)."""
+        out: [shard_count, cap, 9]; counts_out: [shard_count] int32 (device).  Returns (out, counts, stats list).
+        defer_stats=True launches asynchronously (single pass, no host round trip) and returns a token for
+        pool_read_stats() instead of the stats."""
         n = int(demand.shape[0])
         n_stands = int(dist.shape[0])
         cap = n // 2 + 1
@@ -191,7 +193,8 @@ class Engine:
             st = (PoolStats * shard_count)()
             rc = self.lib.td_pool_find_shards(_ptr(demand), n, _ptr(dist), n_stands, pool_size, shard_begin, shard_count,
                                               n_shards, _ptr(out), int(out.shape[1]), _ptr(cnt),
-                                              st if want_stats else None, _ptr(ws), ws.numel(), mf, _stream())
+                                              st if (want_stats and not defer_stats) else None, _ptr(ws), ws.numel(), mf,
+                                              _stream())
             if rc == _lib.TD_ERR_CAPACITY and want_stats:
                 need = sum(int(s.feasible) for s in st)
                 if need > mf:
@@ -199,14 +202,24 @@ class Engine:
                     self._ws[key] = mf
                     continue
             check(rc, "td_pool_find_shards")
-            if want_stats and max_feasible is None and st[0].passes > 1:
+            if want_stats and not defer_stats and max_feasible is None and st[0].passes > 1:
                 # the feasible set did not fit the record list in one pass: remember a capacity that does (bounded
                 # by ~4 GiB per list) so that later calls -- in particular asynchronous ones, which cannot fall back
                 # to cost windows -- run single-pass
                 need = sum(int(s.feasible) for s in st) + 1024
                 self._ws[key] = max(mf, min(need, 1 << 28))
+            if defer_stats:
+                return out, cnt, (ws, shard_count)
             return out, cnt, (list(st) if want_stats else None)
         raise TaxiDispatchError(_lib.TD_ERR_CAPACITY, "td_pool_find_shards")
+
+    def pool_read_stats(self, token):
+        """Completes a defer_stats=True call: waits for the stream, returns (stats list, overflowed)."""
+        ws, shard_count = token
+        st = (PoolStats * shard_count)()
+        ov = ctypes.c_int(0)
+        check(self.lib.td_pool_read_stats(_ptr(ws), shard_count, st, ctypes.byref(ov), _stream()), "td_pool_read_stats")
+        return list(st), bool(ov.value)
 
     def pool_pairs(self, frm: torch.Tensor, to: torch.Tensor, dist: torch.Tensor, accept_all: bool = True,
                    max_loss: float = 1.01):
@@ -411,16 +424,32 @@ def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
     dem = _h2d_i32(dem_np)
     d = _h2d_i32(dist)
     stats = {"evaluated": 0, "feasible": 0, "kept_per_shard": [], "rounds": 0}
+    fast_key = ("pool_single_pass_ok", n, pool_size, n_shards)
+    if n_shards <= 64 and eng._ws.get(fast_key):
+        # steady state: enumeration, selection and merge are queued back to back, ONE host synchronisation
+        out, cnt, token = eng.pool_find_shards(dem, d, pool_size, 0, n_shards, n_shards, defer_stats=True)
+        merged, mcnt = eng.pool_merge_padded(out, cnt, None, n, pool_size)
+        st, overflowed = eng.pool_read_stats(token)
+        if not overflowed:
+            m = int(mcnt.item())
+            stats.update(evaluated=sum(int(s.evaluated) for s in st), feasible=sum(int(s.feasible) for s in st),
+                         rounds=int(st[0].rounds), kept_per_shard=[int(s.kept) for s in st], kept=m)
+            return merged[:m].cpu().numpy(), stats
+        eng._ws[fast_key] = False                         # input outgrew the record list: cost windows below
     parts, counts = [], []
+    single = True
     for b in range(0, n_shards, 64):                       # one call serves up to 64 consecutive shards
         cnt_sh = min(64, n_shards - b)
         out, cnt, st = eng.pool_find_shards(dem, d, pool_size, b, cnt_sh, n_shards)
         parts.append(out)
         counts.append(cnt)
+        single = single and st[0].passes == 1
         stats["evaluated"] += sum(int(s.evaluated) for s in st)
         stats["feasible"] += sum(int(s.feasible) for s in st)
         stats["rounds"] += int(st[0].rounds)
         stats["kept_per_shard"] += [int(s.kept) for s in st]
+    # next time: asynchronous single pass, provided the remembered record capacity can hold every feasible plan
+    eng._ws[fast_key] = n_shards <= 64 and (single or eng._ws.get(("pool_mf", n, pool_size, n_shards), 0) > stats["feasible"])
     slot_plans = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
     slot_counts = counts[0] if len(counts) == 1 else torch.cat(counts, dim=0)
     merged, cnt = eng.pool_merge_padded(slot_plans, slot_counts, None, n, pool_size)
