@@ -57,7 +57,7 @@ struct AsgCtrl {
     unsigned long long stale_cells;   // cells re-read to refresh cached level-0 distances
     long long sfree;                  // sum of the phase lengths D: every still-free row has u = u_init + sfree
     unsigned int nstale, pad3;
-    unsigned long long t_prof[8];     // ns spent by CTA 0 in: scan, sync, settle, sync, phase start, augment (diagnostics)
+    unsigned long long t_prof[16];     // ns spent by CTA 0 in: scan, sync, settle, sync, phase start, augment (diagnostics)
     long long objective;
     int status;
     int pad2;
@@ -191,17 +191,28 @@ __device__ __forceinline__ unsigned long long row_min_reduced(const AsgArgs &a, 
     const int32_t *line = a.cost + size_t(i) * n;
     unsigned long long best = kDistInf;
     if (kVec) {
-        for (int j = lane * 4; j < n; j += 128) {
-            const int4 q = ld_stream_int4(reinterpret_cast<const int4 *>(line + j));
-            const int c[4] = {q.x, q.y, q.z, q.w};
+        // 4 x 16-byte loads in flight per lane (a warp-per-row scan is latency-bound otherwise)
+        for (int j0 = lane * 4; j0 < n; j0 += 512) {
+            int4 q[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long red = (long long)c[k] - a.v[j + k];
-                if (tight_free_only) {
-                    if (red == ui && a.mate_c[j + k] < 0) { const unsigned long long key = rot(j + k); best = key < best ? key : best; }
-                } else {
-                    const unsigned long long key = ((unsigned long long)red << 32) | rot(j + k);
-                    best = key < best ? key : best;
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 128 * u;
+                q[u] = j < n ? ld_stream_int4(reinterpret_cast<const int4 *>(line + j)) : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + 128 * u;
+                if (j >= n) continue;
+                const int c[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const long long red = (long long)c[k] - a.v[j + k];
+                    if (tight_free_only) {
+                        if (red == ui && a.mate_c[j + k] < 0) { const unsigned long long key = rot(j + k); best = key < best ? key : best; }
+                    } else {
+                        const unsigned long long key = ((unsigned long long)red << 32) | rot(j + k);
+                        best = key < best ? key : best;
+                    }
                 }
             }
         }
@@ -248,11 +259,13 @@ assign_kernel(AsgArgs a) {
         ctrl->rows_scanned = 0; ctrl->status = TD_OK; ctrl->gmin[0] = ctrl->gmin[1] = ctrl->gmin[2] = kDistInf;
     }
     grid.sync();
+    tick(-1);
     {   // column minima
         unsigned long long dummy = kDistInf;
         sweep_rows<0, kVec>(a, nullptr, n, gwarp, nwarps, lane, dummy);
     }
     grid.sync();
+    tick(6);
     for (int j = tid; j < n; j += nthreads) a.v[j] = a.vmin[j];
     grid.sync();
     // row minima of the column-reduced costs; every row proposes its first argmin column
@@ -266,6 +279,7 @@ assign_kernel(AsgArgs a) {
         }
     }
     grid.sync();
+    tick(7);
     for (int round = 0;; ++round) {
         // accept: the lowest proposing row takes the column
         for (int i = tid; i < n; i += nthreads) {
@@ -372,6 +386,13 @@ assign_kernel(AsgArgs a) {
                 if (threadIdx.x == 0 && m != kDistInf) atomicMin(&ctrl->gmin[slot], m >> kRowBits);
             }
             if (tid == 0) ctrl->rows_scanned += fc;
+            if (tid == 0) {   // diagnostics: levels and scan time by frontier size (<= 32, <= 256, <= 2048, larger)
+                const int bkt = fc <= 32 ? 0 : (fc <= 256 ? 1 : (fc <= 2048 ? 2 : 3));
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                ctrl->t_prof[8 + bkt] += t - t_last;
+                ctrl->t_prof[12 + bkt] += 1;
+            }
             tick(0);
             grid.sync();
             tick(1);
@@ -552,6 +573,12 @@ extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_o
         if (getenv("TD_ASSIGN_PROF"))
             fprintf(stderr, "[td_assign] us: scan %.0f sync1 %.0f settle %.0f sync2 %.0f phase_start %.0f augment %.0f\n",
                     h.t_prof[0] / 1e3, h.t_prof[1] / 1e3, h.t_prof[2] / 1e3, h.t_prof[3] / 1e3, h.t_prof[4] / 1e3, h.t_prof[5] / 1e3);
+        if (getenv("TD_ASSIGN_PROF"))
+            fprintf(stderr, "[td_assign] init us: column-min sweep %.0f, row-min sweep %.0f\n", h.t_prof[6] / 1e3, h.t_prof[7] / 1e3);
+        if (getenv("TD_ASSIGN_PROF"))
+            fprintf(stderr, "[td_assign] scan us by frontier size <=32: %.0f (%llu levels)  <=256: %.0f (%llu)  <=2048: %.0f (%llu)  >2048: %.0f (%llu)\n",
+                    h.t_prof[8] / 1e3, h.t_prof[12], h.t_prof[9] / 1e3, h.t_prof[13], h.t_prof[10] / 1e3, h.t_prof[14],
+                    h.t_prof[11] / 1e3, h.t_prof[15]);
         if (h.status != TD_OK) return h.status;
     }
     return TD_OK;
