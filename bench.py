@@ -88,7 +88,7 @@ class ClockSampler:
                     self.samples.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -337,10 +337,17 @@ def main():
             traffic = json.load(open(tpath)).get("pool_enum_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    alu_view = None
+    apath = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        alu_view = json.load(open(apath)).get("pool_enum_kernel_alu_view")
+    except Exception:
+        alu_view = None
     roofline = {"bound": "hbm", "kernel": "pool_enum_kernel<4>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_model": "logical: 80 B per evaluated plan + 36 B per feasible plan (SURVEY 8(d)); the kernel is "
                                "INT32-issue / shared-memory bound, compulsory HBM traffic is ~0.4 B per plan",
+                "alu_view_from_ncu": alu_view,
                 "avg_launch_ms": avg_enum_ms, "launches": enum_n, "share_of_step": enum_ms / max(sum(step_ms), 1e-9),
                 "pool_select_share_of_step": sel_ms / max(sum(step_ms), 1e-9)}
 

@@ -42,6 +42,7 @@
 // figure: 80 B per evaluated plan (4 customers x the 5-int32 demand record) + 36 B per feasible plan.
 #include "td_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -1067,6 +1068,7 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
     TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sel_per_sm, pool_select_kernel, kSelThreads, 0));
     if (sel_per_sm < 1) return TD_ERR_CUDA;
     sel_per_sm = sel_per_sm > 4 ? 4 : sel_per_sm;
+    if (const char *e = getenv("TD_SEL_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= sel_per_sm) sel_per_sm = v; }
     if (sms * sel_per_sm < shard_count) return TD_ERR_INVALID;
 
     // the per-pass part of the control block (everything after pass_begin_marker)
