@@ -28,6 +28,7 @@
 // Algorithmic bytes: 4*n^2 (every cost read once).  Actual traffic is higher (transpose + stale
 // rescans) but L2-resident at n = 2000 (16 MB); the kernel is latency/sync-bound, not HBM-bound.
 #include "td_common.cuh"
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -502,7 +503,7 @@ extern "C" int td_lcm(const int32_t *cost, int n, const td_lcm_params *params, i
     // 16-byte loads need aligned lines: n % 4 == 0 and aligned bases (the flag arrays are 16-byte aligned)
     int vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0) ? 1 : 0;
     const size_t smem_need = size_t(n) * 16 + 2 * size_t((n + 15) & ~15) + size_t(2 * n) * 4 + 64;
-    if (smem_need <= 200 * 1024) {
+    if (smem_need <= 200 * 1024 && !getenv("TD_LCM_GENERIC")) {
         // replicated-state kernel: one CTA per SM at most, never more CTAs than a quarter of the lines
         TD_CUDA_TRY(cudaFuncSetAttribute(lcm_rounds_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(200 * 1024)));
         int grid = device_sm_count();

@@ -57,14 +57,16 @@ def _h2d_i32(a, pinned: bool = True) -> torch.Tensor:
         return torch.from_numpy(arr).to("cuda")
     if arr.size > (1 << 22):                       # big matrices: one-off pinned copy
         return torch.from_numpy(arr).pin_memory().to("cuda", non_blocking=True)
-    slot = _PINNED.get(arr.size)
+    bucket = 1 << max(8, int(arr.size - 1).bit_length())        # power-of-two buckets: few allocations
+    slot = _PINNED.get(bucket)
     if slot is None:
-        slot = {"buf": torch.empty(arr.size, dtype=torch.int32).pin_memory(), "ev": None}
-        _PINNED[arr.size] = slot
+        slot = {"buf": torch.empty(bucket, dtype=torch.int32).pin_memory(), "ev": None}
+        _PINNED[bucket] = slot
     if slot["ev"] is not None:
         slot["ev"].synchronize()                   # the previous copy out of this buffer has finished
-    slot["buf"].numpy()[:] = arr.reshape(-1)
-    t = slot["buf"].to("cuda", non_blocking=True).reshape(arr.shape)
+    stage = slot["buf"][: arr.size]
+    stage.numpy()[:] = arr.reshape(-1)
+    t = stage.to("cuda", non_blocking=True).reshape(arr.shape)
     ev = torch.cuda.Event()
     ev.record()
     slot["ev"] = ev
