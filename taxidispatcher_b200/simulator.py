@@ -36,12 +36,22 @@ ID, FROM, TO, CLNT_ASSIGNED, CLNT_ON_BOARD, TIME_STARTED = range(6)
 
 
 class CudaBackend:
-    """The product backend: every primitive runs in libtaxidispatch.so on the GPU."""
+    """The product backend: every primitive runs in libtaxidispatch.so on the GPU.  The cost matrix stays on the
+    device between K1 and the LCM / exact solve that consume it (the host copy is only read by the state machine)."""
 
     def __init__(self):
+        import torch
         from . import dispatch
         self.d = dispatch
+        self.torch = torch
+        self.eng = dispatch.engine()
         self.times = {"pool": 0.0, "cost": 0.0, "lcm": 0.0, "solve": 0.0}
+        self._cost_dev = None      # (id of the host array handed out, device tensor)
+
+    def _device_cost(self, cost):
+        if self._cost_dev is not None and self._cost_dev[0] is cost:
+            return self._cost_dev[1]
+        return self.d._h2d_i32(np.asarray(cost))
 
     def pool_pairs(self, frm, to, dist):
         t0 = time.perf_counter()
@@ -51,21 +61,34 @@ class CudaBackend:
 
     def cost(self, dist, cab_to, cust_from):
         t0 = time.perf_counter()
-        cabs = [(0, 0, int(v)) for v in cab_to]
-        dem = [(0, int(v), 0) for v in cust_from]
-        n, c = self.d.calculate_cost(dist, dem, cabs, fill=BIG_COST, cutoff=DROP_TIME)
+        n = max(len(cab_to), len(cust_from))
+        if n == 0:
+            return np.zeros((0, 0), np.int32)
+        h2d = self.d._h2d_i32
+        empty = self.torch.empty(0, dtype=self.torch.int32, device=self.eng.device)
+        dev = self.eng.cost_matrix(h2d(dist), h2d(cab_to) if len(cab_to) else empty,
+                                   h2d(cust_from) if len(cust_from) else empty, BIG_COST, DROP_TIME)
+        host = dev.cpu().numpy()
+        self._cost_dev = (host, dev)
         self.times["cost"] += time.perf_counter() - t0
-        return np.zeros((0, 0), np.int32) if n == 0 else c
+        return host
 
     def lcm_java(self, cost):
         t0 = time.perf_counter()
-        r = self.d.LCM_java(cost, BIG_COST, MAX_NON_LCM)
+        if len(cost) == 0:
+            return [], BIG_COST
+        r = self.d.Engine.lcm_host_view(*self.eng.lcm(self._device_cost(cost), BIG_COST, stop_at_value=BIG_COST,
+                                                      residual_size=MAX_NON_LCM))          # Simulator.java:523-549
+        mn = r["last_min"]
         self.times["lcm"] += time.perf_counter() - t0
-        return r
+        return list(zip(r["rows"].tolist(), r["cols"].tolist())), (BIG_COST if mn >= BIG_COST else mn)
 
     def solve(self, n, cost):
         t0 = time.perf_counter()
-        x = self.d.solve(n, cost)
+        if n == 0:
+            return []
+        _, _, x, _ = self.eng.assign(self._device_cost(cost), want_x=True)
+        x = x.cpu().numpy()
         self.times["solve"] += time.perf_counter() - t0
         return x
 
