@@ -15,5 +15,4 @@ for n_cabs,n_cust in ((1300,142),(877,172),(900,600),(800,836)):
         a,b=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
         a.record(); r=eng.lcm(c,**kw); b.record(); torch.cuda.synchronize(); ms.append(a.elapsed_time(b))
     h=eng.lcm_host_view(*r)
-    ws=[v for k,v in eng._ws.items() if k==('lcm',n)][0]
     print(n_cabs,n_cust,'n',n,'median ms',round(float(np.median(ms)),3),'pairs',h['n_pairs'])

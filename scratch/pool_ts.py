@@ -7,7 +7,7 @@ dem=torch.from_numpy(g.pool_demand()).cuda(); dist=torch.from_numpy(g.stand_dist
 for rep in range(3):
     out,cnt,st=eng.pool_find_shards(dem,dist,4,0,8,8)
 torch.cuda.synchronize()
-ws=[v for k,v in eng._ws.items() if isinstance(k,tuple) and k[0]=='pool'][0]
+ws=eng._ws['pool']
 ts=ws[:256].cpu().numpy().view(np.uint64)
 t0=int(ts[31]); seq=[int(x) for x in ts[:31] if x>0]
 print('start->first stamp (init+thresholds) us', (seq[0]-t0)/1e3)

@@ -85,9 +85,12 @@ class Engine:
 
     # -- scratch --------------------------------------------------------------------------------
     def _workspace(self, key, nbytes: int) -> torch.Tensor:
+        """One grow-only scratch buffer per operation (calls are stream-ordered, so reuse across sizes is safe)."""
         ws = self._ws.get(key)
         if ws is None or ws.numel() < nbytes:
-            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            ws = None
+            self._ws.pop(key, None)                                   # release before growing
+            ws = torch.empty(max(int(nbytes * 5 // 4), 256), dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
 
@@ -116,7 +119,7 @@ class Engine:
         prm = LcmParams(int(mask_value), int(stop_above), int(stop_at_value), int(sum_below), int(residual_size),
                         int(max_iters))
         nbytes = self.lib.td_lcm_workspace_bytes(n)
-        ws = self._workspace(("lcm", n), nbytes)
+        ws = self._workspace("lcm", nbytes)
         base = scal.data_ptr()
         rc = self.lib.td_lcm(_ptr(cost), n, ctypes.byref(prm), _ptr(rows), _ptr(cols), ctypes.c_void_p(base + 8),
                              ctypes.c_void_p(base), ctypes.c_void_p(base + 12), _ptr(ws), ws.numel(), _stream())
@@ -138,7 +141,7 @@ class Engine:
         obj = torch.zeros(1, dtype=torch.int64, device=self.device)
         x = torch.empty(n * n, dtype=torch.uint8, device=self.device) if want_x else None
         nbytes = self.lib.td_assign_workspace_bytes(n)
-        ws = self._workspace(("assign", n), nbytes)
+        ws = self._workspace("assign", nbytes)
         st = AssignStats() if want_stats else None
         rc = self.lib.td_assign_exact(_ptr(cost), n, _ptr(col), _ptr(obj), _ptr(x),
                                       ctypes.byref(st) if st is not None else None, _ptr(ws), ws.numel(), _stream())
@@ -160,7 +163,7 @@ class Engine:
         mf = int(max_feasible) if max_feasible is not None else self._ws.get(("pool_mf", n, pool_size), 1 << 21)
         for _ in range(8):
             nbytes = self.lib.td_pool_workspace_bytes(n, n_stands, pool_size, mf)
-            ws = self._workspace(("pool", n, n_stands, pool_size), nbytes)
+            ws = self._workspace("pool", nbytes)
             st = PoolStats()
             rc = self.lib.td_pool_find(_ptr(demand), n, _ptr(dist), n_stands, pool_size, shard, n_shards, _ptr(out),
                                        int(out.shape[0]), _ptr(cnt), ctypes.byref(st) if want_stats else None,
@@ -191,7 +194,7 @@ class Engine:
         mf = int(max_feasible) if max_feasible is not None else self._ws.get(key, (1 << 21) * min(shard_count, 4))
         for _ in range(8):
             nbytes = self.lib.td_pool_shards_workspace_bytes(n, n_stands, pool_size, shard_count, mf)
-            ws = self._workspace(("pool", n, n_stands, pool_size, shard_count), nbytes)
+            ws = self._workspace("pool", nbytes)
             st = (PoolStats * shard_count)()
             rc = self.lib.td_pool_find_shards(_ptr(demand), n, _ptr(dist), n_stands, pool_size, shard_begin, shard_count,
                                               n_shards, _ptr(out), int(out.shape[1]), _ptr(cnt),
@@ -231,7 +234,7 @@ class Engine:
         out = torch.empty((cap, 4), dtype=torch.int32, device=self.device)
         cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
         nbytes = self.lib.td_pool_pairs_workspace_bytes(n)
-        ws = self._workspace(("pairs", n), nbytes)
+        ws = self._workspace("pairs", nbytes)
         rc = self.lib.td_pool_pairs(_ptr(frm), _ptr(to), n, _ptr(dist), int(dist.shape[0]), 1 if accept_all else 0,
                                     float(max_loss), _ptr(out), cap, _ptr(cnt), _ptr(ws), ws.numel(), _stream())
         check(rc, "td_pool_pairs")
@@ -241,7 +244,7 @@ class Engine:
         out = torch.empty((max(total, 1), POOL_REC_W), dtype=torch.int32, device=self.device)
         cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
         nbytes = self.lib.td_pool_merge_workspace_bytes(total, n)
-        ws = self._workspace(("merge", total, n), nbytes)
+        ws = self._workspace("merge", nbytes)
         rc = self.lib.td_pool_merge(_ptr(shard_plans), total, n, pool_size, _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(),
                                     _stream())
         check(rc, "td_pool_merge")
@@ -256,7 +259,7 @@ class Engine:
         out = torch.empty((max(total, 1), POOL_REC_W), dtype=torch.int32, device=self.device)
         cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
         nbytes = self.lib.td_pool_merge_workspace_bytes(total, n)
-        ws = self._workspace(("merge", total, n), nbytes)
+        ws = self._workspace("merge", nbytes)
         rc = self.lib.td_pool_merge_padded(_ptr(slot_plans), _ptr(slot_counts), _ptr(slot_shard), n_slots, cap, n, pool_size,
                                            _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(), _stream())
         check(rc, "td_pool_merge_padded")
