@@ -56,7 +56,10 @@ struct AsgCtrl {
     unsigned long long rows_scanned;
     unsigned long long stale_cells;   // cells re-read to refresh cached level-0 distances
     long long sfree;                  // sum of the phase lengths D: every still-free row has u = u_init + sfree
-    unsigned int nstale, pad3;
+    unsigned long long cabs;          // max |c_ij| (init sweep); bounds every potential: |v| <= cabs + sfree, |u| <= 2 cabs + sfree
+    unsigned long long narrow_levels; // relaxation sweeps that ran on the 32-bit path
+    unsigned int ticket[4];           // dynamic unit hand-out of the ring sweeps (slot rotates like gmin)
+    unsigned int nstale, ndone;       // ndone: trees (free rows) that own a sink in the current phase
     unsigned long long t_prof[16];     // ns spent by CTA 0 in: scan, sync, settle, sync, phase start, augment (diagnostics)
     long long objective;
     int status;
@@ -70,17 +73,30 @@ struct AsgArgs {
     int32_t *stale;
     int32_t *vmin; int32_t *mate_r, *mate_c, *root, *claim, *prop, *argcol;
     unsigned long long *distpred; uint8_t *settled;
-    int32_t *frontier[2]; int32_t *sinks;
+    int32_t *frontier[2]; long long *fbase[2]; int32_t *sinks;   // fbase = (distance - u) of the frontier row, same slot
     AsgCtrl *ctrl;
     int32_t *col_of_row_out; long long *objective_out; uint8_t *x_out;
     int max_phases;
+    int force_wide;                   // diagnostics / tests: always use the 64-bit relaxation
+    int deep_permille;                // a phase goes on until this share (per 1000) of its trees has reached a sink
 };
 
+// The predecessor row sits in the low bits through a bijective scramble of [0, 2^24): among rows that offer a column
+// the same distance the winner is then spread over the trees instead of always being the lowest row index, which
+// keeps the trees of a phase balanced (far more of them reach a sink of their own on the reference's degenerate costs).
+#ifndef TD_ASG_SCRAMBLE
+#define TD_ASG_SCRAMBLE 1
+#endif
+constexpr unsigned kRowMask = (1u << kRowBits) - 1;
 __device__ __forceinline__ unsigned long long pack_dp(long long dist, int row) {
-    return ((unsigned long long)dist << kRowBits) | (unsigned)row;
+    const unsigned r = TD_ASG_SCRAMBLE ? (unsigned(row) * 0x3779b1u) & kRowMask : unsigned(row);
+    return ((unsigned long long)dist << kRowBits) | r;
 }
 __device__ __forceinline__ long long dp_dist(unsigned long long k) { return (long long)(k >> kRowBits); }
-__device__ __forceinline__ int dp_row(unsigned long long k) { return int(k & ((1u << kRowBits) - 1)); }
+__device__ __forceinline__ int dp_row(unsigned long long k) {
+    const unsigned r = unsigned(k) & kRowMask;
+    return int(TD_ASG_SCRAMBLE ? (r * 0x8b2f51u) & kRowMask : r);
+}
 
 // One warp relaxes a 256-column tile for a strided group of rows.  rows == nullptr: rows are 0..nrows-1.
 // kMode 0: column minima of the raw costs (init);  kMode 1: Dijkstra relaxation.
@@ -92,6 +108,7 @@ __device__ __forceinline__ void sweep_rows(const AsgArgs &a, const int32_t *rows
     int groups = nwarps / tiles;
     groups = groups < 1 ? 1 : (groups > nrows ? nrows : groups);
     const int units = tiles * groups;
+    int cmx = INT_MIN;   // kMode 0: largest cost seen by this lane
     for (int unit = gwarp; unit < units; unit += nwarps) {
         const int tile = unit % tiles, grp = unit / tiles;
         const int j0 = (tile << 8) + (kVec ? lane * 4 : lane);
@@ -153,6 +170,7 @@ __device__ __forceinline__ void sweep_rows(const AsgArgs &a, const int32_t *rows
                         // order-preserving bias so that negative costs work too
                         const unsigned long long key = (unsigned long long)(unsigned(c[k]) ^ 0x80000000u);
                         best[k] = key < best[k] ? key : best[k];
+                        cmx = c[k] > cmx ? c[k] : cmx;
                     }
                 } else {
 #pragma unroll
@@ -174,6 +192,160 @@ __device__ __forceinline__ void sweep_rows(const AsgArgs &a, const int32_t *rows
                 block_min = best[k] < block_min ? best[k] : block_min;
             }
         }
+    }
+    if (kMode == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const int other = __shfl_xor_sync(0xffffffffu, cmx, o); cmx = other > cmx ? other : cmx; }
+        if (lane == 0 && cmx != INT_MIN) atomicMax(&a.ctrl->cabs, (unsigned long long)(cmx < 0 ? -(long long)cmx : (long long)cmx));
+    }
+}
+
+// ---- cp.async staging --------------------------------------------------------------------------------------------
+// A register-staged sweep keeps 4 KB per warp in flight (64 KB per SM at 128 registers per thread), which caps it at
+// ~2.5-4 TB/s on B200: the loaded HBM latency is ~2 us.  Here every warp owns a ring of kAsgStages stages of 4 cost-row
+// segments (4 x 1 KB) in shared memory, filled with 16-byte cp.async copies that occupy no registers; each lane reads
+// back exactly the bytes it copied, so no barrier is needed -- cp.async.wait_group is the only synchronisation.
+constexpr int kAsgStages = 3;
+constexpr int kAsgStageBytes = 4 * 1024;                                    // 4 rows x 256 columns x int32
+constexpr int kAsgRingBytes = (kAsgThreads / 32) * kAsgStages * kAsgStageBytes;   // 192 KB per CTA
+
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void *g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ int4 lds_int4(unsigned smem_addr) {
+    int4 r;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr) : "memory");
+    return r;
+}
+
+// Tie-breaking of the greedy initial matching (ring passes).  A row with many equally good columns must not always ask
+// for the same one, so every row starts its cyclic column order at its own 256-column tile and its own lane:
+// across tiles the smallest tile_rot wins (atomicMin), inside a tile the first tied lane at or after (hash & 31).
+__device__ __forceinline__ unsigned row_hash(int i) { return unsigned(i) * 2654435761u; }
+__device__ __forceinline__ int pick_lane(unsigned ballot, unsigned h) {
+    const unsigned r = h & 31u;
+    return int((unsigned(__ffs(__funnelshift_r(ballot, ballot, r)) - 1) + r) & 31u);   // ballot != 0
+}
+__device__ __forceinline__ unsigned tile_rot(int col, unsigned h, int n) {
+    const unsigned tiles = unsigned(n + 255) >> 8;
+    const unsigned off = __umulhi(h, tiles) << 8;
+    return unsigned(col) >= off ? unsigned(col) - off : unsigned(col) + (tiles << 8) - off;
+}
+__device__ __forceinline__ int tile_unrot(unsigned rot, unsigned h, int n) {
+    const unsigned tiles = unsigned(n + 255) >> 8;
+    const unsigned c = rot + (__umulhi(h, tiles) << 8);
+    return int(c >= (tiles << 8) ? c - (tiles << 8) : c);
+}
+
+__device__ __forceinline__ int warp_min_i32(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const int other = __shfl_xor_sync(0xffffffffu, v, o); v = other < v ? other : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned warp_min_u32(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned other = __shfl_xor_sync(0xffffffffu, v, o); v = other < v ? other : v; }
+    return v;
+}
+
+// Generic tile sweep through the cp.async ring (n % 4 == 0).  A unit = one 256-column tile x one chunk of consecutive
+// positions of the row list (rows == nullptr: the list is 0..nrows-1); units are numbered chunk-major so that warps
+// working at the same time read neighbouring segments of the same cost rows.  The first nwarps units are assigned
+// statically (small sweeps need no atomics); the rest are handed out through *ticket, because with a static split the
+// slowest warp of a bandwidth-bound sweep finishes 2-3x later than the average one (ncu: two thirds of the samples of a
+// full-matrix sweep were barrier waits).  Results do not depend on which warp runs which unit.
+// unit_begin(j0) sets up the lane's column state, row_fn(pos, row, aux, c[8]) consumes one row (all 32 lanes call it
+// together, so it may shuffle), unit_end(j0) publishes.  aux[pos] (optional, e.g. the row's distance - potential) is
+// fetched one trip ahead, like the row ids, so no load on the path depends on another one.
+__device__ __forceinline__ int ring_chunk_rows(int nrows, int tiles, int nwarps) {
+    // Small sweeps are latency-bound: one unit per warp, all static.  Once a warp would get more than 16 rows the sweep
+    // is bandwidth-bound and is cut into ~4 units per warp (16..64 rows each) for the dynamic hand-out.
+    int groups = nwarps / tiles;
+    groups = groups < 1 ? 1 : groups;
+    const int per = (nrows + groups - 1) / groups;
+    if (per <= 16) return per;
+    int r = ((per + 3) / 4 + 3) & ~3;
+    return r < 16 ? 16 : (r > 64 ? 64 : r);
+}
+
+template <typename UB, typename RF, typename UE>
+__device__ __forceinline__ void ring_sweep(const int32_t *__restrict__ cost, int n, const int32_t *__restrict__ rows,
+                                           const long long *__restrict__ aux, int nrows, int gwarp, int nwarps, int lane,
+                                           unsigned ring, unsigned *ticket, UB unit_begin, RF row_fn, UE unit_end) {
+    if (nrows <= 0) return;
+    const int tiles = (n + 255) >> 8;
+    const int chunk_rows = ring_chunk_rows(nrows, tiles, nwarps);
+    const int chunks = (nrows + chunk_rows - 1) / chunk_rows;
+    const long long units = (long long)tiles * chunks;
+    const unsigned my = ring + unsigned(lane) * 16u;
+    long long unit = gwarp;
+    while (unit < units) {
+        const int tile = int(unit % tiles), chunk = int(unit / tiles);
+        const int j0 = (tile << 8) + lane * 4;
+        const bool lo_in = j0 < n, hi_in = j0 + 128 < n;
+        unit_begin(j0);
+        const int p0 = chunk * chunk_rows;
+        const int my_rows = (nrows - p0) < chunk_rows ? (nrows - p0) : chunk_rows;
+        const int ntrips = (my_rows + 3) >> 2;
+        const int32_t *cbase = cost + j0;
+        auto issue = [&](int trip, const int (&r)[4]) {
+            const unsigned st = my + unsigned(trip % kAsgStages) * kAsgStageBytes;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (r[q] < 0) continue;
+                const int32_t *line = cbase + size_t(r[q]) * n;
+                if (lo_in) cp_async16(st + q * 1024, line);
+                if (hi_in) cp_async16(st + q * 1024 + 512, line + 128);
+            }
+            cp_async_commit();   // possibly empty: keeps the group count uniform
+        };
+        auto ids_of = [&](int trip, int (&r)[4]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = 4 * trip + q;
+                r[q] = e < my_rows ? (rows ? rows[p0 + e] : p0 + e) : -1;
+            }
+        };
+        auto aux_of = [&](int trip, int (&x)[4]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = 4 * trip + q;
+                x[q] = (aux && e < my_rows) ? int(aux[p0 + e]) : 0;
+            }
+        };
+        int ids[4], cur[4], ax[4];
+        ids_of(0, cur);
+        issue(0, cur);
+#pragma unroll
+        for (int t = 1; t < kAsgStages; ++t) { ids_of(t, ids); issue(t, ids); }
+        ids_of(kAsgStages, ids);
+        aux_of(0, ax);
+        for (int trip = 0; trip < ntrips; ++trip) {
+            cp_async_wait<kAsgStages - 1>();
+            const unsigned st = my + unsigned(trip % kAsgStages) * kAsgStageBytes;
+            const int last_q = my_rows - 4 * trip;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q >= last_q) continue;   // warp-uniform
+                const int4 lo = lo_in ? lds_int4(st + q * 1024) : make_int4(0, 0, 0, 0);
+                const int4 hi = hi_in ? lds_int4(st + q * 1024 + 512) : make_int4(0, 0, 0, 0);
+                const int c[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                row_fn(p0 + 4 * trip + q, cur[q], ax[q], c);
+            }
+            issue(trip + kAsgStages, ids);   // refills the stage just consumed (its ids were fetched a trip ago)
+            ids_of(trip + kAsgStages + 1, ids);
+            ids_of(trip + 1, cur);
+            aux_of(trip + 1, ax);
+        }
+        cp_async_wait<0>();
+        unit_end(j0);
+        if (units <= nwarps) break;   // everything was assigned statically
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        unit = (long long)nwarps + __shfl_sync(0xffffffffu, t, 0);
     }
 }
 
@@ -240,6 +412,8 @@ assign_kernel(AsgArgs a) {
     const int lane = threadIdx.x & 31;
     const int gwarp = tid >> 5, nwarps = nthreads >> 5;
     __shared__ unsigned long long s_red[kAsgThreads / 32];
+    extern __shared__ __align__(1024) unsigned char s_ring[];   // kVec only: per-warp cp.async ring
+    const unsigned ring = unsigned(__cvta_generic_to_shared(s_ring)) + unsigned(threadIdx.x >> 5) * (kAsgStages * kAsgStageBytes);
     AsgCtrl *ctrl = a.ctrl;
     unsigned long long t_last = 0;
     auto tick = [&](int k) {   // thread 0 only: accumulate wall time since the previous tick into bucket k
@@ -260,49 +434,174 @@ assign_kernel(AsgArgs a) {
     }
     grid.sync();
     tick(-1);
-    {   // column minima
-        unsigned long long dummy = kDistInf;
-        sweep_rows<0, kVec>(a, nullptr, n, gwarp, nwarps, lane, dummy);
+    // column slots of a lane inside a 256-column tile (ring sweeps): j0..j0+3 and j0+128..j0+131
+    auto slot_col = [](int j0, int k) { return j0 + (k & 3) + ((k >> 2) << 7); };
+    {   // column minima (and max |c| for the 32-bit guard)
+        if (kVec) {
+            int best[8];
+            int cmx = 0;
+            ring_sweep(a.cost, n, nullptr, nullptr, n, gwarp, nwarps, lane, ring, &ctrl->ticket[0],
+                       [&](int) {
+#pragma unroll
+                           for (int k = 0; k < 8; ++k) best[k] = INT_MAX;
+                       },
+                       [&](int, int, int, const int (&c)[8]) {
+#pragma unroll
+                           for (int k = 0; k < 8; ++k) { best[k] = c[k] < best[k] ? c[k] : best[k]; cmx = c[k] > cmx ? c[k] : cmx; }
+                       },
+                       [&](int j0) {
+#pragma unroll
+                           for (int k = 0; k < 8; ++k) {
+                               const int col = slot_col(j0, k);
+                               if (col < n && best[k] < a.vmin[col]) atomicMin(&a.vmin[col], best[k]);
+                           }
+                       });
+            cmx = -warp_min_i32(-cmx);
+            if (lane == 0 && cmx > 0) atomicMax(&ctrl->cabs, (unsigned long long)cmx);
+        } else {
+            unsigned long long dummy = kDistInf;
+            sweep_rows<0, kVec>(a, nullptr, n, gwarp, nwarps, lane, dummy);
+        }
     }
     grid.sync();
     tick(6);
-    for (int j = tid; j < n; j += nthreads) a.v[j] = a.vmin[j];
+    {
+        int vmn = 0;
+        for (int j = tid; j < n; j += nthreads) { const int m = a.vmin[j]; a.v[j] = m; vmn = m < vmn ? m : vmn; }
+        if (vmn < 0) atomicMax(&ctrl->cabs, (unsigned long long)(-(long long)vmn));
+        for (int i = tid; i < n; i += nthreads) a.distpred[i] = kDistInf;   // per-row (minimum, argmin) keys of the next pass
+    }
     grid.sync();
-    // row minima of the column-reduced costs; every row proposes its first argmin column
-    for (int i = gwarp; i < n; i += nwarps) {
-        const unsigned long long k = row_min_reduced<kVec>(a, i, lane, false, 0);
-        if (lane == 0) {
+    // c - v and u - (c - v) stay inside 32 bits when max |c| < 2^29; otherwise the 64-bit row scans are used
+    const bool init_ring = kVec && ctrl->cabs < (1ull << 29);
+    // row minima of the column-reduced costs; every row proposes its first argmin column (cyclic order from a
+    // row-dependent offset, so that rows with many equally good columns spread their proposals)
+    if (init_ring) {
+        int nv[8], uj0 = 0;
+        bool in[8];
+        ring_sweep(a.cost, n, nullptr, nullptr, n, gwarp, nwarps, lane, ring, &ctrl->ticket[1],
+                   [&](int j0) {
+                       uj0 = j0;
+#pragma unroll
+                       for (int k = 0; k < 8; ++k) { const int col = slot_col(j0, k); in[k] = col < n; nv[k] = in[k] ? -int(a.v[col]) : 0; }
+                   },
+                   [&](int, int i, int, const int (&c)[8]) {
+                       int val[8], lm = INT_MAX;
+#pragma unroll
+                       for (int k = 0; k < 8; ++k) { val[k] = in[k] ? c[k] + nv[k] : INT_MAX; lm = val[k] < lm ? val[k] : lm; }
+                       const int m = warp_min_i32(lm);
+                       const unsigned h = row_hash(i);
+                       if (lane == pick_lane(__ballot_sync(0xffffffffu, lm == m), h)) {
+                           int col = 0;
+#pragma unroll
+                           for (int k = 7; k >= 0; --k) col = val[k] == m ? slot_col(uj0, k) : col;
+                           atomicMin(&a.distpred[i], ((unsigned long long)unsigned(m) << 32) | tile_rot(col, h, n));
+                       }
+                   },
+                   [&](int) {});
+        grid.sync();
+        for (int i = tid; i < n; i += nthreads) {
+            const unsigned long long k = a.distpred[i];
             a.u[i] = (long long)(k >> 32);
-            const int j = int((unsigned(k) + row_offset(i, n)) % unsigned(n));
+            const int j = tile_unrot(unsigned(k), row_hash(i), n);
             a.argcol[i] = j;
             atomicMin(&a.prop[j], i);
+        }
+    } else {
+        for (int i = gwarp; i < n; i += nwarps) {
+            const unsigned long long k = row_min_reduced<kVec>(a, i, lane, false, 0);
+            if (lane == 0) {
+                a.u[i] = (long long)(k >> 32);
+                const int j = int((unsigned(k) + row_offset(i, n)) % unsigned(n));
+                a.argcol[i] = j;
+                atomicMin(&a.prop[j], i);
+            }
         }
     }
     grid.sync();
     tick(7);
     for (int round = 0;; ++round) {
-        // accept: the lowest proposing row takes the column
-        for (int i = tid; i < n; i += nthreads) {
-            if (a.mate_r[i] >= 0) continue;
-            const int j = a.argcol[i];
-            if (j >= 0 && a.prop[j] == i) { a.mate_r[i] = j; a.mate_c[j] = i; }
+        // accept: the lowest proposing row takes the column; the others are listed (row, u) for the next round
+        const int lst = round & 1;
+        for (int base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
+            const int i = base + threadIdx.x;
+            bool lost = false;
+            if (i < n && a.mate_r[i] < 0) {
+                const int j = a.argcol[i];
+                if (j >= 0 && a.prop[j] == i) { a.mate_r[i] = j; a.mate_c[j] = i; }
+                else lost = true;
+            }
+            if (init_ring) {
+                const unsigned ball = __ballot_sync(0xffffffffu, lost);
+                unsigned wb = 0;
+                if (lane == 0 && ball) wb = atomicAdd(&ctrl->fcount[lst], __popc(ball));
+                wb = __shfl_sync(0xffffffffu, wb, 0);
+                if (lost) {
+                    const unsigned slot_i = wb + __popc(ball & ((1u << lane) - 1));
+                    a.frontier[lst][slot_i] = i;
+                    a.fbase[lst][slot_i] = a.u[i];
+                    a.claim[i] = -1;   // = UINT_MAX: no tight free column found yet
+                }
+            }
         }
         grid.sync();
         if (round == kGreedyRounds - 1) break;
         for (int j = tid; j < n; j += nthreads) a.prop[j] = INT_MAX;
+        if (tid == 0) { ctrl->fcount[lst ^ 1] = 0; ctrl->ticket[lst] = 0; }
         grid.sync();
         // losers look for their first tight column that is still free
-        for (int i = gwarp; i < n; i += nwarps) {
-            if (a.mate_r[i] >= 0) continue;
-            const unsigned long long k = row_min_reduced<kVec>(a, i, lane, true, a.u[i]);
-            if (lane == 0) {
-                const int j = (k == kDistInf) ? -1 : int((unsigned(k) + row_offset(i, n)) % unsigned(n));
+        if (init_ring) {
+            const int nlost = int(ctrl->fcount[lst]);
+            int nv[8], uj0 = 0;
+            bool in[8];
+            ring_sweep(a.cost, n, a.frontier[lst], a.fbase[lst], nlost, gwarp, nwarps, lane, ring, &ctrl->ticket[lst],
+                       [&](int j0) {
+                           uj0 = j0;
+#pragma unroll
+                           for (int k = 0; k < 8; ++k) {
+                               const int col = slot_col(j0, k);
+                               in[k] = col < n && a.mate_c[col < n ? col : 0] < 0;
+                               nv[k] = in[k] ? -int(a.v[col]) : 0;
+                           }
+                       },
+                       [&](int, int i, int ui, const int (&c)[8]) {
+                           bool tight[8], any = false;
+#pragma unroll
+                           for (int k = 0; k < 8; ++k) { tight[k] = in[k] && c[k] + nv[k] == ui; any = any || tight[k]; }
+                           const unsigned ball = __ballot_sync(0xffffffffu, any);
+                           if (ball == 0) return;
+                           const unsigned h = row_hash(i);
+                           if (lane == pick_lane(ball, h)) {
+                               int col = 0;
+#pragma unroll
+                               for (int k = 7; k >= 0; --k) col = tight[k] ? slot_col(uj0, k) : col;
+                               atomicMin(reinterpret_cast<unsigned *>(&a.claim[i]), tile_rot(col, h, n));
+                           }
+                       },
+                       [&](int) {});
+            grid.sync();
+            for (int t = tid; t < nlost; t += nthreads) {
+                const int i = a.frontier[lst][t];
+                const unsigned cand = unsigned(a.claim[i]);
+                const int j = cand == 0xffffffffu ? -1 : tile_unrot(cand, row_hash(i), n);
                 a.argcol[i] = j;
                 if (j >= 0) atomicMin(&a.prop[j], i);
+            }
+        } else {
+            for (int i = gwarp; i < n; i += nwarps) {
+                if (a.mate_r[i] >= 0) continue;
+                const unsigned long long k = row_min_reduced<kVec>(a, i, lane, true, a.u[i]);
+                if (lane == 0) {
+                    const int j = (k == kDistInf) ? -1 : int((unsigned(k) + row_offset(i, n)) % unsigned(n));
+                    a.argcol[i] = j;
+                    if (j >= 0) atomicMin(&a.prop[j], i);
+                }
             }
         }
         grid.sync();
     }
+    if (tid == 0) { ctrl->fcount[0] = ctrl->fcount[1] = 0; ctrl->ticket[0] = ctrl->ticket[1] = ctrl->ticket[2] = 0; }
+    grid.sync();
 
     for (int i = tid; i < n; i += nthreads) { a.uinit[i] = a.u[i]; a.vinit[i] = a.v[i]; }
     // ================= phases ===================================================================
@@ -310,6 +609,7 @@ assign_kernel(AsgArgs a) {
     for (int phase = 0;; ++phase) {
         // ---- P0: reset search state, frontier = all free rows ---------------------------------
         tick(-1);
+        if (tid == 0) { ctrl->nsinks = 0; ctrl->ndone = 0; }
         for (int j = tid; j < n; j += nthreads) { a.distpred[j] = kDistInf; a.settled[j] = 0; }
         for (int base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
             const int i = base + threadIdx.x;
@@ -324,7 +624,11 @@ assign_kernel(AsgArgs a) {
             unsigned wb = 0;
             if (lane == 0 && ball) wb = atomicAdd(&ctrl->fcount[0], __popc(ball));
             wb = __shfl_sync(0xffffffffu, wb, 0);
-            if (is_free) a.frontier[0][wb + __popc(ball & ((1u << lane) - 1))] = i;
+            if (is_free) {
+                const unsigned slot_i = wb + __popc(ball & ((1u << lane) - 1));
+                a.frontier[0][slot_i] = i;
+                a.fbase[0][slot_i] = -a.u[i];
+            }
         }
         grid.sync();
         const unsigned nfree = ctrl->fcount[0];
@@ -369,14 +673,62 @@ assign_kernel(AsgArgs a) {
         }
 
         int cur = 0;
-        long long dstar = 0;
+        long long dstar = 0, last_delta = 0;
+        // a phase does not stop at the first sink: it keeps growing the forest (distances stay exact, every
+        // settled node is included in the dual update, so all forest edges become tight) until this many trees
+        // own a sink; each of them is augmented.  Fewer phases, and a phase never scans a row twice.
+        unsigned want_done = unsigned((unsigned long long)nfree * unsigned(a.deep_permille) / 1000u);
+        want_done = want_done < 1u ? 1u : want_done;
         tick(4);
         for (int level = 0;; ++level) {
             const int slot = level % 3;
             // ---- (a) relax: every frontier row against all unsettled columns ------------------
             const unsigned fc = (phase > 0 && level == 0) ? 0u : ctrl->fcount[cur];   // level 0 comes from the cache
             unsigned long long bmin = kDistInf;
-            sweep_rows<1, kVec>(a, a.frontier[cur], int(fc), gwarp, nwarps, lane, bmin);
+            // 32-bit guard: every (distance - u - v + c) of this level is below 4 cabs + 2 sfree + last_delta
+            const bool narrow = kVec && !a.force_wide &&
+                                4 * ctrl->cabs + 2 * (unsigned long long)ctrl->sfree + (unsigned long long)last_delta < (1ull << 30);
+            if (narrow && kVec) {
+                // 32-bit relaxation through the cp.async ring: one IADD3 + compare/select pair per cost cell instead of
+                // the ~13 integer instructions of the 64-bit (distance, predecessor) keys of sweep_rows
+                int nv[8], best[8], brow[8];
+                bool act[8];
+                const bool small_sweep = ring_chunk_rows(int(fc), (n + 255) >> 8, nwarps) <= 16 && fc > 0;
+                ring_sweep(a.cost, n, a.frontier[cur], a.fbase[cur], int(fc), gwarp, nwarps, lane, ring, &ctrl->ticket[slot],
+                           [&](int j0) {
+#pragma unroll
+                               for (int k = 0; k < 8; ++k) {
+                                   const int col = slot_col(j0, k);
+                                   act[k] = col < n && !a.settled[col < n ? col : 0];
+                                   nv[k] = act[k] ? -int(a.v[col]) : 0;
+                                   best[k] = INT_MAX;
+                                   brow[k] = 0;
+                               }
+                           },
+                           [&](int, int i, int base, const int (&c)[8]) {
+#pragma unroll
+                               for (int k = 0; k < 8; ++k) {
+                                   const int val = c[k] + base + nv[k];
+                                   if (val < best[k]) { best[k] = val; brow[k] = i; }
+                               }
+                           },
+                           [&](int j0) {
+#pragma unroll
+                               for (int k = 0; k < 8; ++k) {
+                                   if (!act[k] || best[k] == INT_MAX) continue;
+                                   const int col = slot_col(j0, k);
+                                   const unsigned long long key = pack_dp((long long)best[k], brow[k]);
+                                   // small (latency-bound) sweeps skip the pre-check load; a candidate that does not
+                                   // improve its column cannot lower the level minimum below the true one either
+                                   if (small_sweep || key < a.distpred[col]) {
+                                       atomicMin(&a.distpred[col], key);
+                                       bmin = key < bmin ? key : bmin;
+                                   }
+                               }
+                           });
+            }
+            else sweep_rows<1, kVec>(a, a.frontier[cur], int(fc), gwarp, nwarps, lane, bmin);
+            if (tid == 0 && narrow) ctrl->narrow_levels += 1;
             bmin = warp_min_u64(bmin);
             if (lane == 0) s_red[threadIdx.x >> 5] = bmin;
             __syncthreads();
@@ -398,8 +750,16 @@ assign_kernel(AsgArgs a) {
             tick(1);
             // ---- (b) settle every column at the new minimum distance -------------------------
             const unsigned long long dl = ctrl->gmin[slot];
-            if (dl == kDistInf) { if (tid == 0) ctrl->status = TD_ERR_NOT_CONVERGED; dstar = -1; break; }
+            if (dl == kDistInf) {
+                // nothing left to settle: the forest is complete.  Fine when some tree already owns a sink.
+                if (ctrl->ndone > 0) { dstar = last_delta; break; }
+                if (tid == 0) ctrl->status = TD_ERR_NOT_CONVERGED;
+                dstar = -1;
+                break;
+            }
+            if (level > 2 * n + 16) { if (tid == 0) ctrl->status = TD_ERR_NOT_CONVERGED; dstar = -1; break; }   // cannot happen
             const long long delta = (long long)dl;
+            last_delta = delta;
             unsigned long long carry = kDistInf;
             for (int base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
                 const int j = base + threadIdx.x;
@@ -415,6 +775,8 @@ assign_kernel(AsgArgs a) {
                             mate = a.mate_c[j];
                             if (mate < 0) {
                                 a.sinks[atomicAdd(&ctrl->nsinks, 1u)] = j;
+                                // one augmenting path per tree: the smallest sink column wins (order-independent)
+                                if (atomicMin(&a.claim[a.root[dp_row(k)]], j) == INT_MAX) atomicAdd(&ctrl->ndone, 1u);
                             } else {
                                 a.drow[mate] = delta;
                                 a.root[mate] = a.root[dp_row(k)];
@@ -429,27 +791,26 @@ assign_kernel(AsgArgs a) {
                 unsigned wb = 0;
                 if (lane == 0 && ball) wb = atomicAdd(&ctrl->fcount[cur ^ 1], __popc(ball));
                 wb = __shfl_sync(0xffffffffu, wb, 0);
-                if (push) a.frontier[cur ^ 1][wb + __popc(ball & ((1u << lane) - 1))] = mate;
+                if (push) {
+                    const unsigned slot_i = wb + __popc(ball & ((1u << lane) - 1));
+                    a.frontier[cur ^ 1][slot_i] = mate;
+                    a.fbase[cur ^ 1][slot_i] = delta - a.u[mate];
+                }
             }
             carry = warp_min_u64(carry);
             if (lane == 0 && carry != kDistInf) atomicMin(&ctrl->gmin[(level + 1) % 3], carry);
-            if (tid == 0) { ctrl->gmin[(level + 2) % 3] = kDistInf; ctrl->levels += 1; }
+            if (tid == 0) { ctrl->gmin[(level + 2) % 3] = kDistInf; ctrl->ticket[(level + 2) % 3] = 0; ctrl->levels += 1; }
             tick(2);
             grid.sync();
             tick(3);
             if (tid == 0) ctrl->fcount[cur] = 0;  // consumed; becomes the target two levels from now
-            if (ctrl->nsinks > 0) { dstar = delta; break; }
+            if (ctrl->ndone >= want_done) { dstar = delta; break; }
             cur ^= 1;
         }
         if (dstar < 0) break;
 
         // ---- augment: one sink per tree, smallest column index wins ---------------------------
         const unsigned ns = ctrl->nsinks;
-        for (unsigned s = tid; s < ns; s += nthreads) {
-            const int j = a.sinks[s];
-            atomicMin(&a.claim[a.root[dp_row(a.distpred[j])]], j);
-        }
-        grid.sync();
         for (unsigned s = tid; s < ns; s += nthreads) {
             int j = a.sinks[s];
             if (a.claim[a.root[dp_row(a.distpred[j])]] != j) continue;
@@ -471,8 +832,10 @@ assign_kernel(AsgArgs a) {
         for (int j = tid; j < n; j += nthreads)
             if (a.settled[j]) a.v[j] -= dstar - dp_dist(a.distpred[j]);
         if (tid == 0) {
-            ctrl->nsinks = 0; ctrl->fcount[0] = ctrl->fcount[1] = 0; ctrl->phases += 1; ctrl->sfree += dstar;
+            // nsinks / ndone are reset at the start of the next phase: slower CTAs may still be reading them here
+            ctrl->fcount[0] = ctrl->fcount[1] = 0; ctrl->phases += 1; ctrl->sfree += dstar;
             ctrl->gmin[0] = ctrl->gmin[1] = ctrl->gmin[2] = kDistInf;
+            ctrl->ticket[0] = ctrl->ticket[1] = ctrl->ticket[2] = 0;
         }
         grid.sync();
         tick(5);
@@ -508,6 +871,7 @@ static AsgArgs carve_assign(void *ws, int n, size_t *bytes) {
     a.vmin = c.take<int32_t>(nn); a.mate_r = c.take<int32_t>(nn); a.mate_c = c.take<int32_t>(nn);
     a.root = c.take<int32_t>(nn); a.claim = c.take<int32_t>(nn); a.prop = c.take<int32_t>(nn); a.argcol = c.take<int32_t>(nn);
     a.frontier[0] = c.take<int32_t>(nn); a.frontier[1] = c.take<int32_t>(nn); a.sinks = c.take<int32_t>(nn);
+    a.fbase[0] = c.take<long long>(nn); a.fbase[1] = c.take<long long>(nn);
     a.settled = c.take<uint8_t>(nn);
     *bytes = c.used();
     return a;
@@ -538,13 +902,21 @@ extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_o
     AsgArgs a = carve_assign(workspace, n, &bytes);
     a.cost = cost; a.n = n; a.col_of_row_out = col_of_row_out; a.objective_out = reinterpret_cast<long long *>(objective_out);
     a.x_out = x_out; a.max_phases = n + 8;
+    a.deep_permille = 20;
+    if (const char *e = getenv("TD_ASSIGN_DEEP")) a.deep_permille = atoi(e);
+    if (const char *e = getenv("TD_ASSIGN_WIDE")) a.force_wide = atoi(e);
     TD_CUDA_TRY(cudaMemsetAsync(a.ctrl, 0, sizeof(AsgCtrl), st));
     if (x_out) TD_CUDA_TRY(cudaMemsetAsync(x_out, 0, size_t(n) * n, st));
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
     void *kern = vec ? (void *)assign_kernel<true> : (void *)assign_kernel<false>;
     int per_sm = 0;
-    if (vec) TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assign_kernel<true>, kAsgThreads, 0));
-    else TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assign_kernel<false>, kAsgThreads, 0));
+    const size_t dyn_smem = vec ? size_t(kAsgRingBytes) : 0;
+    if (vec) {
+        TD_CUDA_TRY(cudaFuncSetAttribute(assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
+        TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assign_kernel<true>, kAsgThreads, dyn_smem));
+    } else {
+        TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assign_kernel<false>, kAsgThreads, 0));
+    }
     if (per_sm < 1) return TD_ERR_CUDA;
     per_sm = per_sm > 2 ? 2 : per_sm;
     int grid = device_sm_count() * per_sm;
@@ -555,7 +927,7 @@ extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_o
     void *args[] = {(void *)&a};
     {
         ProfScope prof(TD_PROF_ASSIGN, st);
-        TD_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kAsgThreads), args, 0, st));
+        TD_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kAsgThreads), args, dyn_smem, st));
     }
     count_launch();
     if (stats) {
@@ -573,6 +945,8 @@ extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_o
         if (getenv("TD_ASSIGN_PROF"))
             fprintf(stderr, "[td_assign] us: scan %.0f sync1 %.0f settle %.0f sync2 %.0f phase_start %.0f augment %.0f\n",
                     h.t_prof[0] / 1e3, h.t_prof[1] / 1e3, h.t_prof[2] / 1e3, h.t_prof[3] / 1e3, h.t_prof[4] / 1e3, h.t_prof[5] / 1e3);
+        if (getenv("TD_ASSIGN_PROF"))
+            fprintf(stderr, "[td_assign] max|c| %llu, 32-bit relaxation sweeps %llu of %u\n", h.cabs, h.narrow_levels, h.levels);
         if (getenv("TD_ASSIGN_PROF"))
             fprintf(stderr, "[td_assign] init us: column-min sweep %.0f, row-min sweep %.0f\n", h.t_prof[6] / 1e3, h.t_prof[7] / 1e3);
         if (getenv("TD_ASSIGN_PROF"))
