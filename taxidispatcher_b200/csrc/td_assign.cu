@@ -58,6 +58,7 @@ struct AsgCtrl {
     long long sfree;                  // sum of the phase lengths D: every still-free row has u = u_init + sfree
     unsigned long long cabs;          // max |c_ij| (init sweep); bounds every potential: |v| <= cabs + sfree, |u| <= 2 cabs + sfree
     unsigned long long narrow_levels; // relaxation sweeps that ran on the 32-bit path
+    unsigned int ncarry, pad4;        // rows of surviving trees that open the next phase
     unsigned int ticket[4];           // dynamic unit hand-out of the ring sweeps (slot rotates like gmin)
     unsigned int nstale, ndone;       // ndone: trees (free rows) that own a sink in the current phase
     unsigned long long t_prof[16];     // ns spent by CTA 0 in: scan, sync, settle, sync, phase start, augment (diagnostics)
@@ -73,11 +74,13 @@ struct AsgArgs {
     int32_t *stale;
     int32_t *vmin; int32_t *mate_r, *mate_c, *root, *claim, *prop, *argcol;
     unsigned long long *distpred; uint8_t *settled;
-    int32_t *frontier[2]; long long *fbase[2]; int32_t *sinks;   // fbase = (distance - u) of the frontier row, same slot
+    int32_t *frontier[2]; long long *fbase[2]; int32_t *carry; long long *cbase; int32_t *sinks;   // fbase = (distance - u) of the frontier row, same slot
     AsgCtrl *ctrl;
     int32_t *col_of_row_out; long long *objective_out; uint8_t *x_out;
     int max_phases;
     int force_wide;                   // diagnostics / tests: always use the 64-bit relaxation
+    int carry_min_levels;             // ... only after a phase of at least this many levels
+    int carry_forest;                 // keep the trees that were not augmented into the next phase (see P0)
     int deep_permille;                // a phase goes on until this share (per 1000) of its trees has reached a sink
 };
 
@@ -606,28 +609,46 @@ assign_kernel(AsgArgs a) {
     for (int i = tid; i < n; i += nthreads) { a.uinit[i] = a.u[i]; a.vinit[i] = a.v[i]; }
     // ================= phases ===================================================================
     bool first_phase = true;
+    bool keep_forest = false;
     for (int phase = 0;; ++phase) {
         // ---- P0: reset search state, frontier = all free rows ---------------------------------
         tick(-1);
         if (tid == 0) { ctrl->nsinks = 0; ctrl->ndone = 0; }
-        for (int j = tid; j < n; j += nthreads) { a.distpred[j] = kDistInf; a.settled[j] = 0; }
+        // Trees that were not augmented survive into this phase (carry_forest): after the dual update all their edges
+        // are tight, so their rows sit at distance 0 and their columns stay settled with the same predecessors; the
+        // rows are relaxed again in ONE bandwidth-bound sweep at level 0 instead of being re-discovered tight edge by
+        // tight edge over dozens of latency-bound levels.  The end of the previous phase left drow = 0 / settled = 1 /
+        // distpred = (0, predecessor) on exactly those nodes.
+        const bool carried = keep_forest;   // decided at the end of the previous phase
+        for (int j = tid; j < n; j += nthreads) {
+            if (!carried || !a.settled[j]) { a.distpred[j] = kDistInf; a.settled[j] = 0; }
+        }
         for (int base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
             const int i = base + threadIdx.x;
-            bool is_free = false;
+            bool is_free = false, is_carry = false;
             if (i < n) {
                 a.claim[i] = INT_MAX;
                 is_free = a.mate_r[i] < 0;
-                a.drow[i] = is_free ? 0 : kRowInf;
-                if (is_free) a.root[i] = i;
+                if (is_free) { a.drow[i] = 0; a.root[i] = i; }
+                else if (carried && a.drow[i] == 0) is_carry = true;
+                else a.drow[i] = kRowInf;
             }
             const unsigned ball = __ballot_sync(0xffffffffu, is_free);
-            unsigned wb = 0;
+            const unsigned ballc = __ballot_sync(0xffffffffu, is_carry);
+            unsigned wb = 0, wc = 0;
             if (lane == 0 && ball) wb = atomicAdd(&ctrl->fcount[0], __popc(ball));
+            if (lane == 0 && ballc) wc = atomicAdd(&ctrl->ncarry, __popc(ballc));
             wb = __shfl_sync(0xffffffffu, wb, 0);
+            wc = __shfl_sync(0xffffffffu, wc, 0);
             if (is_free) {
                 const unsigned slot_i = wb + __popc(ball & ((1u << lane) - 1));
                 a.frontier[0][slot_i] = i;
                 a.fbase[0][slot_i] = -a.u[i];
+            }
+            if (is_carry) {
+                const unsigned slot_i = wc + __popc(ballc & ((1u << lane) - 1));
+                a.carry[slot_i] = i;
+                a.cbase[slot_i] = -a.u[i];
             }
         }
         grid.sync();
@@ -662,9 +683,10 @@ assign_kernel(AsgArgs a) {
             const long long sfree = ctrl->sfree;
             unsigned long long lmin = kDistInf;
             for (int j = tid; j < n; j += nthreads) {
+                if (a.settled[j]) continue;   // column of a surviving tree
                 const unsigned long long b = a.base0[j];
                 const long long d0 = dp_dist(b) + a.vinit[j] - a.v[j] - sfree;
-                a.distpred[j] = pack_dp(d0, dp_row(b));
+                atomicMin(&a.distpred[j], pack_dp(d0, dp_row(b)));   // the level-0 sweep of the carried rows may run already
                 lmin = (unsigned long long)d0 < lmin ? (unsigned long long)d0 : lmin;
             }
             lmin = warp_min_u64(lmin);
@@ -672,7 +694,7 @@ assign_kernel(AsgArgs a) {
             if (tid == 0) ctrl->nstale = 0;
         }
 
-        int cur = 0;
+        int cur = 0, nlevels = 0;
         long long dstar = 0, last_delta = 0;
         // a phase does not stop at the first sink: it keeps growing the forest (distances stay exact, every
         // settled node is included in the dual update, so all forest edges become tight) until this many trees
@@ -683,7 +705,11 @@ assign_kernel(AsgArgs a) {
         for (int level = 0;; ++level) {
             const int slot = level % 3;
             // ---- (a) relax: every frontier row against all unsettled columns ------------------
-            const unsigned fc = (phase > 0 && level == 0) ? 0u : ctrl->fcount[cur];   // level 0 comes from the cache
+            // level 0 of a later phase: the free rows come from the cache, the rows of surviving trees are swept
+            const bool from_carry = phase > 0 && level == 0;
+            const unsigned fc = from_carry ? ctrl->ncarry : ctrl->fcount[cur];
+            const int32_t *lrows = from_carry ? a.carry : a.frontier[cur];
+            const long long *lbase = from_carry ? a.cbase : a.fbase[cur];
             unsigned long long bmin = kDistInf;
             // 32-bit guard: every (distance - u - v + c) of this level is below 4 cabs + 2 sfree + last_delta
             const bool narrow = kVec && !a.force_wide &&
@@ -694,7 +720,7 @@ assign_kernel(AsgArgs a) {
                 int nv[8], best[8], brow[8];
                 bool act[8];
                 const bool small_sweep = ring_chunk_rows(int(fc), (n + 255) >> 8, nwarps) <= 16 && fc > 0;
-                ring_sweep(a.cost, n, a.frontier[cur], a.fbase[cur], int(fc), gwarp, nwarps, lane, ring, &ctrl->ticket[slot],
+                ring_sweep(a.cost, n, lrows, lbase, int(fc), gwarp, nwarps, lane, ring, &ctrl->ticket[slot],
                            [&](int j0) {
 #pragma unroll
                                for (int k = 0; k < 8; ++k) {
@@ -727,7 +753,7 @@ assign_kernel(AsgArgs a) {
                                }
                            });
             }
-            else sweep_rows<1, kVec>(a, a.frontier[cur], int(fc), gwarp, nwarps, lane, bmin);
+            else sweep_rows<1, kVec>(a, lrows, int(fc), gwarp, nwarps, lane, bmin);
             if (tid == 0 && narrow) ctrl->narrow_levels += 1;
             bmin = warp_min_u64(bmin);
             if (lane == 0) s_red[threadIdx.x >> 5] = bmin;
@@ -804,11 +830,16 @@ assign_kernel(AsgArgs a) {
             grid.sync();
             tick(3);
             if (tid == 0) ctrl->fcount[cur] = 0;  // consumed; becomes the target two levels from now
+            nlevels = level + 1;
             if (ctrl->ndone >= want_done) { dstar = delta; break; }
             cur ^= 1;
         }
         if (dstar < 0) break;
 
+        // Surviving trees are kept for the next phase only when this phase was deep: re-discovering a deep forest costs
+        // one latency-bound level per tight edge on the way, while shallow phases (easy instances) are better off with
+        // freshly balanced trees.
+        keep_forest = a.carry_forest != 0 && nlevels >= a.carry_min_levels;
         // ---- augment: one sink per tree, smallest column index wins ---------------------------
         const unsigned ns = ctrl->nsinks;
         for (unsigned s = tid; s < ns; s += nthreads) {
@@ -827,15 +858,25 @@ assign_kernel(AsgArgs a) {
         // potentials: every forest edge becomes tight, feasibility is kept
         for (int i = tid; i < n; i += nthreads) {
             const long long d = a.drow[i];
-            if (d != kRowInf) a.u[i] += dstar - d;
+            if (d != kRowInf) {
+                a.u[i] += dstar - d;
+                // rows of trees that found no sink stay in the forest (distance 0 after this update)
+                a.drow[i] = (keep_forest && a.claim[a.root[i]] == INT_MAX) ? 0 : kRowInf;
+            }
         }
-        for (int j = tid; j < n; j += nthreads)
-            if (a.settled[j]) a.v[j] -= dstar - dp_dist(a.distpred[j]);
+        for (int j = tid; j < n; j += nthreads) {
+            if (!a.settled[j]) continue;
+            const unsigned long long k = a.distpred[j];
+            a.v[j] -= dstar - dp_dist(k);
+            // distpred of a column on an augmenting path is still being read by the flip above: only survivors are rewritten
+            if (keep_forest && a.claim[a.root[dp_row(k)]] == INT_MAX) a.distpred[j] = pack_dp(0, dp_row(k));
+            else a.settled[j] = 0;
+        }
         if (tid == 0) {
             // nsinks / ndone are reset at the start of the next phase: slower CTAs may still be reading them here
             ctrl->fcount[0] = ctrl->fcount[1] = 0; ctrl->phases += 1; ctrl->sfree += dstar;
             ctrl->gmin[0] = ctrl->gmin[1] = ctrl->gmin[2] = kDistInf;
-            ctrl->ticket[0] = ctrl->ticket[1] = ctrl->ticket[2] = 0;
+            ctrl->ticket[0] = ctrl->ticket[1] = ctrl->ticket[2] = 0; ctrl->ncarry = 0;
         }
         grid.sync();
         tick(5);
@@ -872,6 +913,7 @@ static AsgArgs carve_assign(void *ws, int n, size_t *bytes) {
     a.root = c.take<int32_t>(nn); a.claim = c.take<int32_t>(nn); a.prop = c.take<int32_t>(nn); a.argcol = c.take<int32_t>(nn);
     a.frontier[0] = c.take<int32_t>(nn); a.frontier[1] = c.take<int32_t>(nn); a.sinks = c.take<int32_t>(nn);
     a.fbase[0] = c.take<long long>(nn); a.fbase[1] = c.take<long long>(nn);
+    a.carry = c.take<int32_t>(nn); a.cbase = c.take<long long>(nn);
     a.settled = c.take<uint8_t>(nn);
     *bytes = c.used();
     return a;
@@ -905,6 +947,10 @@ extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_o
     a.deep_permille = 20;
     if (const char *e = getenv("TD_ASSIGN_DEEP")) a.deep_permille = atoi(e);
     if (const char *e = getenv("TD_ASSIGN_WIDE")) a.force_wide = atoi(e);
+    a.carry_forest = 1;
+    if (const char *e = getenv("TD_ASSIGN_CARRY")) a.carry_forest = atoi(e);
+    a.carry_min_levels = 4;
+    if (const char *e = getenv("TD_ASSIGN_CARRY_MIN")) a.carry_min_levels = atoi(e);
     TD_CUDA_TRY(cudaMemsetAsync(a.ctrl, 0, sizeof(AsgCtrl), st));
     if (x_out) TD_CUDA_TRY(cudaMemsetAsync(x_out, 0, size_t(n) * n, st));
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
