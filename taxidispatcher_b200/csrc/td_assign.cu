@@ -91,9 +91,11 @@ struct AsgArgs {
 #define TD_ASG_SCRAMBLE 1
 #endif
 constexpr unsigned kRowMask = (1u << kRowBits) - 1;
+__device__ __forceinline__ unsigned scramble_row(int row) {
+    return TD_ASG_SCRAMBLE ? (unsigned(row) * 0x3779b1u) & kRowMask : unsigned(row);
+}
 __device__ __forceinline__ unsigned long long pack_dp(long long dist, int row) {
-    const unsigned r = TD_ASG_SCRAMBLE ? (unsigned(row) * 0x3779b1u) & kRowMask : unsigned(row);
-    return ((unsigned long long)dist << kRowBits) | r;
+    return ((unsigned long long)dist << kRowBits) | scramble_row(row);
 }
 __device__ __forceinline__ long long dp_dist(unsigned long long k) { return (long long)(k >> kRowBits); }
 __device__ __forceinline__ int dp_row(unsigned long long k) {
@@ -226,11 +228,16 @@ __device__ __forceinline__ int4 lds_int4(unsigned smem_addr) {
 
 // Tie-breaking of the greedy initial matching (ring passes).  A row with many equally good columns must not always ask
 // for the same one, so every row starts its cyclic column order at its own 256-column tile and its own lane:
-// across tiles the smallest tile_rot wins (atomicMin), inside a tile the first tied lane at or after (hash & 31).
+// across tiles the smallest tile_rot wins (atomicMin), inside a tile the first tied lane at or after (hash & 31), inside
+// the lane the first tied slot at or after ((hash >> 5) & 7).
 __device__ __forceinline__ unsigned row_hash(int i) { return unsigned(i) * 2654435761u; }
 __device__ __forceinline__ int pick_lane(unsigned ballot, unsigned h) {
     const unsigned r = h & 31u;
     return int((unsigned(__ffs(__funnelshift_r(ballot, ballot, r)) - 1) + r) & 31u);   // ballot != 0
+}
+__device__ __forceinline__ int pick_slot(unsigned mask8, unsigned h) {   // first set bit at or after (h >> 5) & 7, cyclic
+    const unsigned s = (h >> 5) & 7u;
+    return int((unsigned(__ffs(((mask8 | (mask8 << 8)) >> s) & 0xffu) - 1) + s) & 7u);   // mask8 != 0
 }
 __device__ __forceinline__ unsigned tile_rot(int col, unsigned h, int n) {
     const unsigned tiles = unsigned(n + 255) >> 8;
@@ -495,9 +502,10 @@ assign_kernel(AsgArgs a) {
                        const int m = warp_min_i32(lm);
                        const unsigned h = row_hash(i);
                        if (lane == pick_lane(__ballot_sync(0xffffffffu, lm == m), h)) {
-                           int col = 0;
+                           unsigned mask = 0;
 #pragma unroll
-                           for (int k = 7; k >= 0; --k) col = val[k] == m ? slot_col(uj0, k) : col;
+                           for (int k = 0; k < 8; ++k) mask |= val[k] == m ? (1u << k) : 0u;
+                           const int col = slot_col(uj0, pick_slot(mask, h));
                            atomicMin(&a.distpred[i], ((unsigned long long)unsigned(m) << 32) | tile_rot(col, h, n));
                        }
                    },
@@ -575,9 +583,10 @@ assign_kernel(AsgArgs a) {
                            if (ball == 0) return;
                            const unsigned h = row_hash(i);
                            if (lane == pick_lane(ball, h)) {
-                               int col = 0;
+                               unsigned mask = 0;
 #pragma unroll
-                               for (int k = 7; k >= 0; --k) col = tight[k] ? slot_col(uj0, k) : col;
+                               for (int k = 0; k < 8; ++k) mask |= tight[k] ? (1u << k) : 0u;
+                               const int col = slot_col(uj0, pick_slot(mask, h));
                                atomicMin(reinterpret_cast<unsigned *>(&a.claim[i]), tile_rot(col, h, n));
                            }
                        },
@@ -717,7 +726,9 @@ assign_kernel(AsgArgs a) {
             if (narrow && kVec) {
                 // 32-bit relaxation through the cp.async ring: one IADD3 + compare/select pair per cost cell instead of
                 // the ~13 integer instructions of the 64-bit (distance, predecessor) keys of sweep_rows
-                int nv[8], best[8], brow[8];
+                int nv[8], best[8];
+                unsigned bsr[8];   // scrambled predecessor row: (distance, scrambled row) is minimised lexicographically,
+                                   // so the result does not depend on the order of the frontier list or on the chunking
                 bool act[8];
                 const bool small_sweep = ring_chunk_rows(int(fc), (n + 255) >> 8, nwarps) <= 16 && fc > 0;
                 ring_sweep(a.cost, n, lrows, lbase, int(fc), gwarp, nwarps, lane, ring, &ctrl->ticket[slot],
@@ -728,14 +739,15 @@ assign_kernel(AsgArgs a) {
                                    act[k] = col < n && !a.settled[col < n ? col : 0];
                                    nv[k] = act[k] ? -int(a.v[col]) : 0;
                                    best[k] = INT_MAX;
-                                   brow[k] = 0;
+                                   bsr[k] = kRowMask;
                                }
                            },
                            [&](int, int i, int base, const int (&c)[8]) {
+                               const unsigned sr = scramble_row(i);
 #pragma unroll
                                for (int k = 0; k < 8; ++k) {
                                    const int val = c[k] + base + nv[k];
-                                   if (val < best[k]) { best[k] = val; brow[k] = i; }
+                                   if (val < best[k] || (val == best[k] && sr < bsr[k])) { best[k] = val; bsr[k] = sr; }
                                }
                            },
                            [&](int j0) {
@@ -743,7 +755,7 @@ assign_kernel(AsgArgs a) {
                                for (int k = 0; k < 8; ++k) {
                                    if (!act[k] || best[k] == INT_MAX) continue;
                                    const int col = slot_col(j0, k);
-                                   const unsigned long long key = pack_dp((long long)best[k], brow[k]);
+                                   const unsigned long long key = ((unsigned long long)(long long)best[k] << kRowBits) | bsr[k];
                                    // small (latency-bound) sweeps skip the pre-check load; a candidate that does not
                                    // improve its column cannot lower the level minimum below the true one either
                                    if (small_sweep || key < a.distpred[col]) {

@@ -256,6 +256,38 @@ def test_assign_random_small(td, n):
     _check_assign(td, rng.integers(-50, 50, (n, n)))            # negative costs
 
 
+@pytest.mark.parametrize("n", [4, 8, 128, 132, 256, 260, 508, 1024])
+def test_assign_ring_path_sizes(td, n):
+    """n % 4 == 0 takes the cp.async ring sweeps: partial tiles, half-tiles, one and several tiles"""
+    rng = np.random.default_rng(300 + n)
+    _check_assign(td, rng.integers(1, 40, (n, n)))
+    _check_assign(td, rng.integers(0, 3, (n, n)))
+    _check_assign(td, rng.integers(-1000, 250001, (n, n)))
+    _check_assign(td, np.abs(rng.integers(0, 50, n)[:, None] - rng.integers(0, 50, n)[None, :]))   # stand-derived, degenerate
+
+
+@pytest.mark.parametrize("n", [64, 200, 301])
+def test_assign_large_magnitudes_take_the_64_bit_sweeps(td, n):
+    """4 max|c| + 2 sum(D) + level >= 2^30 switches a level to the 64-bit relaxation; max|c| >= 2^29 also the init"""
+    rng = np.random.default_rng(400 + n)
+    _check_assign(td, rng.integers(0, 2**28 + 12345, (n, n)))          # 32-bit init, 64-bit relaxation
+    _check_assign(td, rng.integers(-2**30, 2**30, (n, n)))             # 64-bit everywhere
+    c = rng.integers(1, 40, (n, n))
+    c[rng.integers(0, n, 5)] = 2**30                                    # a few huge dummy rows
+    _check_assign(td, c)
+
+
+def test_assign_is_deterministic(td):
+    dist, cab_to, cust_from = g.config1b()
+    n, cost = cost_ref.calculate_cost_np(dist, cab_to, cust_from)
+    cols = [td.solve_full(n, cost)[1].tolist() for _ in range(3)]
+    assert cols[0] == cols[1] == cols[2]
+    c2 = g.config2_stand()
+    a = td.solve_full(c2.shape[0], c2)[1]
+    b = td.solve_full(c2.shape[0], c2)[1]
+    assert np.array_equal(a, b)
+
+
 def test_assign_structured(td):
     rng = np.random.default_rng(77)
     for n_cabs, n_cust, S, cutoff in ((120, 200, 50, None), (200, 120, 50, 10), (218, 600, 50, 10), (600, 351, 50, 10)):
