@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small, deterministic driver for ncu captures: one invocation of each hot-path kernel on its
 BASELINE.json shape.  Usage (on the GPU box, see profiles/README.md):
-    python profiles/prof_driver.py [pool] [cost] [lcm] [assign5a] [assign2s]
+    python profiles/prof_driver.py [pool] [cost] [lcm] [assign5a] [assign5b] [assign2s]
 """
 import os
 import sys
@@ -39,6 +39,10 @@ if "assign5a" in which:
     c = torch.from_numpy(g.config5a()).cuda()
     col, obj, _, st = eng.assign(c, want_stats=True)
     print("assign5a", int(obj.item()), st.phases, st.search_steps, st.rows_scanned)
+if "assign5b" in which:
+    c = torch.from_numpy(g.config5b_cost()).cuda()
+    col, obj, _, st = eng.assign(c, want_stats=True)
+    print("assign5b", int(obj.item()), st.phases, st.search_steps, st.rows_scanned)
 if "assign2s" in which:
     c = torch.from_numpy(g.config2_stand()).cuda()
     col, obj, _, st = eng.assign(c, want_stats=True)

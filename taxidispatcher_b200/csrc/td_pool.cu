@@ -320,6 +320,7 @@ pool_enum_kernel(EnumArgs a) {
     WarpOut wo{0xffffffffu, unsigned(kChunk), false};
     __shared__ unsigned s_hist[kEnumThreads / 32][kBuckets];   // per-warp cost histogram of the warp's current shard
     unsigned *whist = s_hist[threadIdx.x >> 5];
+    __shared__ int s_stage[kEnumThreads / 32][64];                 // K = 4: third pickups and offsets of the current batch
     for (int b = lane; b < kBuckets; b += 32) whist[b] = 0;
     __syncwarp();
     auto flush_counts = [&]() {
@@ -426,40 +427,70 @@ pool_enum_kernel(EnumArgs a) {
             continue;
         }
 
-        // K == 4: warp-uniform loop over p2, lanes over p3
+        // K == 4: the (third pickup, last pickup) pairs of the item are flattened over the lanes.  With lanes over the
+        // last pickup only, the candidate prefixes (a few dozen entries) left a third of the lanes idle (ncu: 22 of 32
+        // threads active per instruction).  Per batch of 32 third pickups: lane l prepares candidate b2 + l (validity,
+        // length n3 of its last-pickup prefix), a warp scan turns the lengths into offsets, and every lane then takes
+        // flat pair indices f, f + 32, ... and finds its (third, last) by a 5-step search over the 32 offsets.
         const int n2 = cand_count(a.cnt, c1.x, a01);
-        for (int t2 = 0; t2 < n2; ++t2) {
-            const int p2 = a.list[size_t(c1.x) * n + t2];
-            if (p2 == p0 || p2 == p1 || (al && !al[p2])) continue;
-            if (a01 >= kTbl && a.slack[size_t(c1.x) * n + t2] < a01) continue;
-            const int4 c2 = cust[p2];
-            const int a12 = D(c1.x, c2.x);
-            const int w2 = a01 + a12;
-            const int t02 = D(c0.y, c2.y), t20 = D(c2.y, c0.y), t12 = D(c1.y, c2.y), t21 = D(c2.y, c1.y);
-            const int n3 = cand_count(a.cnt, c2.x, w2);
-            for (int t3 = lane; t3 < ((n3 + 31) & ~31); t3 += 32) {
-                bool valid = t3 < n3;
-                int p3 = 0;
+        int *st_p2 = s_stage[threadIdx.x >> 5], *st_end = st_p2 + 32;
+        for (int b2 = 0; b2 < n2; b2 += 32) {
+            const int t2 = b2 + lane;
+            int p2l = -1, n3l = 0;
+            if (t2 < n2) {
+                p2l = a.list[size_t(c1.x) * n + t2];
+                bool ok = p2l != p0 && p2l != p1 && (!al || al[p2l]);
+                if (ok && a01 >= kTbl) ok = a.slack[size_t(c1.x) * n + t2] >= a01;
+                if (ok) n3l = cand_count(a.cnt, cust[p2l].x, a01 + D(c1.x, cust[p2l].x));
+                else p2l = -1;
+            }
+            int incl = n3l;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            st_p2[lane] = p2l;
+            st_end[lane] = incl;
+            __syncwarp();
+            for (int f0 = 0; f0 < total; f0 += 32) {
+                const int f = f0 + lane;
+                bool valid = f < total;
+                int sidx = 0;
                 if (valid) {
+#pragma unroll
+                    for (int stp = 16; stp > 0; stp >>= 1)
+                        if (st_end[sidx + stp - 1] <= f) sidx += stp;
+                }
+                int nfeas = 0, best = INT_MAX, p2 = 0, p3 = 0;
+                if (valid) {
+                    p2 = st_p2[sidx];
+                    const int t3 = f - (sidx ? st_end[sidx - 1] : 0);
+                    const int4 c2 = cust[p2];
+                    const int a12 = D(c1.x, c2.x);
+                    const int w2 = a01 + a12;
                     p3 = a.list[size_t(c2.x) * n + t3];
                     valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2 < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2) &&
                             (!al || al[p3]);
-                }
-                int nfeas = 0, best = INT_MAX;
-                if (valid) {
-                    const int4 c3 = cust[p3];
-                    const int a23 = D(c2.x, c3.x);
-                    int e[4], t[4][4], sl[4];
-                    e[0] = D(c3.x, c0.y); e[1] = D(c3.x, c1.y); e[2] = D(c3.x, c2.y); e[3] = D(c3.x, c3.y);
-                    t[0][0] = t[1][1] = t[2][2] = t[3][3] = 0;
-                    t[0][1] = t01; t[1][0] = t10; t[0][2] = t02; t[2][0] = t20; t[1][2] = t12; t[2][1] = t21;
-                    t[0][3] = D(c0.y, c3.y); t[3][0] = D(c3.y, c0.y);
-                    t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
-                    t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
-                    sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - w2 - a23;
-                    eval4(e, t, sl, w2 + a23, nfeas, best);
-                    my_eval += 24;
-                    my_feas += nfeas;
+                    if (valid) {
+                        const int4 c3 = cust[p3];
+                        const int a23 = D(c2.x, c3.x);
+                        int e[4], t[4][4], sl[4];
+                        e[0] = D(c3.x, c0.y); e[1] = D(c3.x, c1.y); e[2] = D(c3.x, c2.y); e[3] = D(c3.x, c3.y);
+                        t[0][0] = t[1][1] = t[2][2] = t[3][3] = 0;
+                        t[0][1] = t01; t[1][0] = t10;
+                        t[0][2] = D(c0.y, c2.y); t[2][0] = D(c2.y, c0.y);
+                        t[1][2] = D(c1.y, c2.y); t[2][1] = D(c2.y, c1.y);
+                        t[0][3] = D(c0.y, c3.y); t[3][0] = D(c3.y, c0.y);
+                        t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
+                        t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
+                        sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - w2 - a23;
+                        eval4(e, t, sl, w2 + a23, nfeas, best);
+                        my_eval += 24;
+                        my_feas += nfeas;
+                    }
                 }
                 emit_records(a, wo, nfeas > 0, make_rank(p0, p1, p2, p3, best & 31), best >> kPermBits, lane, whist);
             }
