@@ -800,39 +800,40 @@ assign_kernel(AsgArgs a) {
             last_delta = delta;
             unsigned long long carry = kDistInf;
             for (int base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
+                // all loads of a step are independent of each other: three round trips per level (state, tree data,
+                // frontier slot) instead of one per dependent access
                 const int j = base + threadIdx.x;
-                bool push = false;
-                int mate = -1;
-                if (phase == 0 && level == 0 && j < n) a.base0[j] = a.distpred[j];   // sfree = 0, v = v_init here
-                if (j < n && !a.settled[j]) {
-                    const unsigned long long k = a.distpred[j];
-                    if (k != kDistInf) {
-                        const long long d = dp_dist(k);
-                        if (d == delta) {
-                            a.settled[j] = 1;
-                            mate = a.mate_c[j];
-                            if (mate < 0) {
-                                a.sinks[atomicAdd(&ctrl->nsinks, 1u)] = j;
-                                // one augmenting path per tree: the smallest sink column wins (order-independent)
-                                if (atomicMin(&a.claim[a.root[dp_row(k)]], j) == INT_MAX) atomicAdd(&ctrl->ndone, 1u);
-                            } else {
-                                a.drow[mate] = delta;
-                                a.root[mate] = a.root[dp_row(k)];
-                                push = true;
-                            }
-                        } else {
-                            carry = (unsigned long long)d < carry ? (unsigned long long)d : carry;
-                        }
-                    }
+                const bool inb = j < n;
+                const bool was_settled = inb ? a.settled[j] != 0 : true;
+                const unsigned long long k = inb ? a.distpred[j] : kDistInf;
+                const int mate = inb ? a.mate_c[j] : -1;
+                if (phase == 0 && level == 0 && inb) a.base0[j] = k;   // sfree = 0, v = v_init here
+                bool now = false;
+                if (!was_settled && k != kDistInf) {
+                    const long long d = dp_dist(k);
+                    now = d == delta;
+                    if (!now) carry = (unsigned long long)d < carry ? (unsigned long long)d : carry;
                 }
+                const bool push = now && mate >= 0, sink = now && mate < 0;
+                int root_p = 0;
+                long long u_mate = 0;
+                if (now) root_p = a.root[dp_row(k)];
+                if (push) u_mate = a.u[mate];
                 const unsigned ball = __ballot_sync(0xffffffffu, push);
                 unsigned wb = 0;
                 if (lane == 0 && ball) wb = atomicAdd(&ctrl->fcount[cur ^ 1], __popc(ball));
+                if (now) a.settled[j] = 1;
+                if (sink) {
+                    a.sinks[atomicAdd(&ctrl->nsinks, 1u)] = j;
+                    // one augmenting path per tree: the smallest sink column wins (order-independent)
+                    if (atomicMin(&a.claim[root_p], j) == INT_MAX) atomicAdd(&ctrl->ndone, 1u);
+                }
+                if (push) { a.drow[mate] = delta; a.root[mate] = root_p; }
                 wb = __shfl_sync(0xffffffffu, wb, 0);
                 if (push) {
                     const unsigned slot_i = wb + __popc(ball & ((1u << lane) - 1));
                     a.frontier[cur ^ 1][slot_i] = mate;
-                    a.fbase[cur ^ 1][slot_i] = delta - a.u[mate];
+                    a.fbase[cur ^ 1][slot_i] = delta - u_mate;
                 }
             }
             carry = warp_min_u64(carry);
