@@ -10,28 +10,42 @@
 // on the number of distinct reduced path lengths, not on n:
 //
 //   init      v_j = min_i c_ij ; u_i = min_j (c_ij - v_j) ; greedy matching on tight cells
-//             (each row proposes its first tight free column, lowest row wins; a few rounds).
-//             From here on  r_ij = c_ij - u_i - v_j >= 0  and matched cells have r = 0.
+//             (each row proposes a tight free column picked by a row hash, lowest row wins; 4 rounds,
+//             the losers rescan only their own rows).  From here on  r_ij = c_ij - u_i - v_j >= 0
+//             and matched cells have r = 0.
 //   phase     multi-source Dijkstra from ALL free rows at once.  Costs are integers, so the
 //             priority queue is a sequence of levels (Dial): one level = (a) every row that
 //             entered the forest at the previous level relaxes all unsettled columns with one
-//             coalesced pass over its cost row (warp tiles of 256 columns, 64-bit atomicMin of
-//             (distance, predecessor row) per column), (b) all columns at the new minimum distance
+//             coalesced pass over its cost row, (b) all columns at the new minimum distance
 //             are settled together; matched ones pull their mate row into the forest, free ones
-//             are sinks.  The phase ends at the first level that reaches a sink; potentials are
-//             updated (u_i += D - d_i on forest rows, v_j -= D - dist_j on settled columns), which
-//             makes every forest edge tight, and one augmenting path per tree is flipped (trees
-//             are vertex-disjoint because every column has one predecessor and every matched row
-//             one parent column).  Each phase matches at least one more row.
+//             are sinks.  A phase goes on until 2 % of its trees own a sink (distances stay exact and
+//             every settled node takes part in the dual update, so all forest edges become tight);
+//             potentials are updated (u_i += D - d_i on forest rows, v_j -= D - dist_j on settled
+//             columns) and one augmenting path per tree is flipped (trees are vertex-disjoint
+//             because every column has one predecessor and every matched row one parent column).
+//   carry     after a deep phase the trees that were not augmented stay: their rows are at distance 0
+//             under the new potentials, so the next phase relaxes them in ONE bandwidth-bound sweep
+//             at level 0 instead of re-discovering them tight edge by tight edge; the free rows
+//             themselves are never rescanned (their column minima are cached, see P0).
 //   finish    objective = sum c[i][mate(i)] in int64; optional dense x in the reference layout.
 //
 // Exactness: potentials stay feasible and matched cells stay tight through every step, so when
 // the matching is perfect, complementary slackness gives optimality for any integer costs
 // (ties included) -- no epsilon, no scaling, no price wars on the reference's tiny cost ranges.
+// The matching itself is deterministic: every choice among ties is a minimum over an order that
+// does not depend on scheduling.
 //
-// Everything runs in ONE cooperative persistent kernel (grid = resident CTAs of all 148 SMs);
+// Data path (n % 4 == 0): cost rows are staged through a per-warp ring of 3 x 4 KB shared-memory
+// stages filled by 16-byte cp.async copies (192 KB per CTA, no registers held by loads in flight),
+// the arithmetic is 32-bit whenever 4 max|c| + 2 sum(D) + level < 2^30, and sweep units (256-column
+// tile x up to 64 rows) are handed out dynamically.  Other shapes / magnitudes take the register-staged
+// 64-bit sweeps (sweep_rows, row_min_reduced).
+//
+// Everything runs in ONE cooperative persistent kernel (one 512-thread CTA per SM);
 // steps are separated by grid.sync().  Algorithmic bytes: 4n bytes per row relaxed; the solver
 // reports rows_scanned so achieved GB/s = 4 n rows_scanned / time.
+// Diagnostics (environment, read per call): TD_ASSIGN_PROF=1 prints in-kernel timers; TD_ASSIGN_DEEP
+// (per-mille of trees per phase), TD_ASSIGN_CARRY, TD_ASSIGN_CARRY_MIN, TD_ASSIGN_WIDE override the defaults.
 #include "td_common.cuh"
 #include <string.h>
 #include <stdio.h>
