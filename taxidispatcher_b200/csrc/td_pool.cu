@@ -455,44 +455,60 @@ pool_enum_kernel(EnumArgs a) {
             st_p2[lane] = p2l;
             st_end[lane] = incl;
             __syncwarp();
+            // one (third, last) pair per lane: evaluate all 24 drop-off orders, materialise the best feasible one
+            auto eval_pair = [&](bool valid, int p2, const int4 c2, int a12, int t02, int t20, int t12, int t21, int t3) {
+                int nfeas = 0, best = INT_MAX, p3 = 0;
+                const int w2 = a01 + a12;
+                if (valid) {
+                    p3 = a.list[size_t(c2.x) * n + t3];
+                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2 < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2) &&
+                            (!al || al[p3]);
+                }
+                if (valid) {
+                    const int4 c3 = cust[p3];
+                    const int a23 = D(c2.x, c3.x);
+                    int e[4], t[4][4], sl[4];
+                    e[0] = D(c3.x, c0.y); e[1] = D(c3.x, c1.y); e[2] = D(c3.x, c2.y); e[3] = D(c3.x, c3.y);
+                    t[0][0] = t[1][1] = t[2][2] = t[3][3] = 0;
+                    t[0][1] = t01; t[1][0] = t10; t[0][2] = t02; t[2][0] = t20; t[1][2] = t12; t[2][1] = t21;
+                    t[0][3] = D(c0.y, c3.y); t[3][0] = D(c3.y, c0.y);
+                    t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
+                    t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
+                    sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - w2 - a23;
+                    eval4(e, t, sl, w2 + a23, nfeas, best);
+                    my_eval += 24;
+                    my_feas += nfeas;
+                }
+                emit_records(a, wo, nfeas > 0, make_rank(p0, p1, p2, p3, best & 31), best >> kPermBits, lane, whist);
+            };
+            const int n_valid = __popc(__ballot_sync(0xffffffffu, p2l >= 0));
+            if (total >= 96 * n_valid) {
+                // long last-pickup prefixes (thousands of customers): lanes over the last pickup keep >= 3 of 4 warps
+                // full, and the per-third-pickup lookups are done once per warp instead of once per pair
+                for (int sidx = 0; sidx < 32; ++sidx) {
+                    const int p2 = st_p2[sidx];
+                    if (p2 < 0) continue;   // warp-uniform
+                    const int n3 = st_end[sidx] - (sidx ? st_end[sidx - 1] : 0);
+                    const int4 c2 = cust[p2];
+                    const int a12 = D(c1.x, c2.x);
+                    const int t02 = D(c0.y, c2.y), t20 = D(c2.y, c0.y), t12 = D(c1.y, c2.y), t21 = D(c2.y, c1.y);
+                    for (int t3 = lane; t3 < ((n3 + 31) & ~31); t3 += 32) eval_pair(t3 < n3, p2, c2, a12, t02, t20, t12, t21, t3);
+                }
+                continue;
+            }
             for (int f0 = 0; f0 < total; f0 += 32) {
                 const int f = f0 + lane;
-                bool valid = f < total;
+                const bool valid = f < total;
                 int sidx = 0;
                 if (valid) {
 #pragma unroll
                     for (int stp = 16; stp > 0; stp >>= 1)
                         if (st_end[sidx + stp - 1] <= f) sidx += stp;
                 }
-                int nfeas = 0, best = INT_MAX, p2 = 0, p3 = 0;
-                if (valid) {
-                    p2 = st_p2[sidx];
-                    const int t3 = f - (sidx ? st_end[sidx - 1] : 0);
-                    const int4 c2 = cust[p2];
-                    const int a12 = D(c1.x, c2.x);
-                    const int w2 = a01 + a12;
-                    p3 = a.list[size_t(c2.x) * n + t3];
-                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2 < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2) &&
-                            (!al || al[p3]);
-                    if (valid) {
-                        const int4 c3 = cust[p3];
-                        const int a23 = D(c2.x, c3.x);
-                        int e[4], t[4][4], sl[4];
-                        e[0] = D(c3.x, c0.y); e[1] = D(c3.x, c1.y); e[2] = D(c3.x, c2.y); e[3] = D(c3.x, c3.y);
-                        t[0][0] = t[1][1] = t[2][2] = t[3][3] = 0;
-                        t[0][1] = t01; t[1][0] = t10;
-                        t[0][2] = D(c0.y, c2.y); t[2][0] = D(c2.y, c0.y);
-                        t[1][2] = D(c1.y, c2.y); t[2][1] = D(c2.y, c1.y);
-                        t[0][3] = D(c0.y, c3.y); t[3][0] = D(c3.y, c0.y);
-                        t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
-                        t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
-                        sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - w2 - a23;
-                        eval4(e, t, sl, w2 + a23, nfeas, best);
-                        my_eval += 24;
-                        my_feas += nfeas;
-                    }
-                }
-                emit_records(a, wo, nfeas > 0, make_rank(p0, p1, p2, p3, best & 31), best >> kPermBits, lane, whist);
+                const int p2 = valid ? st_p2[sidx] : p0;
+                const int t3 = f - (sidx ? st_end[sidx - 1] : 0);
+                const int4 c2 = cust[p2];
+                eval_pair(valid, p2, c2, D(c1.x, c2.x), D(c0.y, c2.y), D(c2.y, c0.y), D(c1.y, c2.y), D(c2.y, c1.y), t3);
             }
         }
     }

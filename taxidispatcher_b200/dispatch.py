@@ -279,16 +279,12 @@ def engine() -> Engine:
 # ================================================================================================
 # reference-shaped host API
 # ================================================================================================
-def calculate_cost(distances, demand: Sequence, cabs: Sequence, fill: int = BIG_COST, cutoff: Optional[int] = None,
-                   as_list: bool = False):
-    """split.py:123-136: (n, cost) with cost[c_idx][d_idx] = distances[cab.to][customer.from],
-    square-padded with `fill` (big_cost).  cutoff=DROP_TIME gives simulate.py:27 / Simulator.java:509.
-    demand / cabs are lists of (id, from, to); indexing is positional.  n == 0 -> (0, 0)
-    (simulate.py:21).  cost is an int32 ndarray (list of rows with as_list=True)."""
+def _cost_device(distances, demand: Sequence, cabs: Sequence, fill: int, cutoff: Optional[int]):
+    """Device-resident cost matrix of calculate_cost (None when n == 0)."""
     n_cabs, n_cust = len(cabs), len(demand)
     n = max(n_cabs, n_cust)
     if n == 0:
-        return 0, 0
+        return 0, None
     eng = engine()
     dist = _h2d_i32(distances)
     cab_to = _h2d_i32([c[2] for c in cabs]) if n_cabs else torch.empty(0, dtype=torch.int32, device=eng.device)
@@ -297,7 +293,19 @@ def calculate_cost(distances, demand: Sequence, cabs: Sequence, fill: int = BIG_
         s = int(dist.shape[0])
         if int(cab_to.max()) >= s or int(cab_to.min()) < 0 or int(cust_from.max()) >= s or int(cust_from.min()) < 0:
             raise IndexError("stand index out of range of the distance table")  # the reference raises IndexError too
-    cost = eng.cost_matrix(dist, cab_to, cust_from, fill, cutoff).cpu().numpy()
+    return n, eng.cost_matrix(dist, cab_to, cust_from, fill, cutoff)
+
+
+def calculate_cost(distances, demand: Sequence, cabs: Sequence, fill: int = BIG_COST, cutoff: Optional[int] = None,
+                   as_list: bool = False):
+    """split.py:123-136: (n, cost) with cost[c_idx][d_idx] = distances[cab.to][customer.from],
+    square-padded with `fill` (big_cost).  cutoff=DROP_TIME gives simulate.py:27 / Simulator.java:509.
+    demand / cabs are lists of (id, from, to); indexing is positional.  n == 0 -> (0, 0)
+    (simulate.py:21).  cost is an int32 ndarray (list of rows with as_list=True)."""
+    n, cost_d = _cost_device(distances, demand, cabs, fill, cutoff)
+    if n == 0:
+        return 0, 0
+    cost = cost_d.cpu().numpy()
     return n, (cost.tolist() if as_list else cost)
 
 
@@ -320,11 +328,13 @@ def solve(n: int, cost):
 
 
 def solve_dispatch(distances, demand, cabs, fill: int = BIG_COST, cutoff: Optional[int] = None):
-    """split.py:139-155 / simulate.py:36-53: (n, x, cost).  n == 0 -> (0, [], 0) (simulate.py:38)."""
-    n, cost = calculate_cost(distances, demand, cabs, fill, cutoff)
+    """split.py:139-155 / simulate.py:36-53: (n, x, cost).  n == 0 -> (0, [], 0) (simulate.py:38).
+    The cost matrix goes from K1 to K2 on the device; the host copy is only the returned value."""
+    n, cost_d = _cost_device(distances, demand, cabs, fill, cutoff)
     if n == 0:
         return 0, [], 0
-    return n, solve(n, cost), cost
+    _, _, x, _ = engine().assign(cost_d, want_x=True)
+    return n, x.cpu().numpy(), cost_d.cpu().numpy()
 
 
 def LCM(n: int, c, mask_value: int = BIG_COST, stop_above: int = INT32_MAX, stop_at_value: int = INT32_MAX,
