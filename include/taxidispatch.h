@@ -135,6 +135,18 @@ int td_assign_exact(const int32_t *cost, int n,
                     uint8_t *x_out /* n*n or NULL */, td_assign_stats *stats /* host, may be NULL */,
                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* Unbalanced-native variant.  Every real call of the reference is unbalanced: the cost
+ * matrix is padded to n = max(cabs, customers) with constant `big_cost` rows or columns (split.py:123-136,
+ * Simulator.java:493-520; simulog_solv.txt: supply 600 vs demand 218-368).  cost is still that padded n x n
+ * matrix and all outputs keep the padded layout, but only the real rows / columns are searched: rows
+ * n_real_rows..n-1 (or columns n_real_cols..n-1) MUST be constant, they receive the leftover columns (rows) in
+ * index order.  The objective equals td_assign_exact's.  One of n_real_rows, n_real_cols must be n. */
+size_t td_assign_rect_workspace_bytes(int n, int n_real_rows, int n_real_cols);
+int td_assign_exact_rect(const int32_t *cost, int n, int n_real_rows, int n_real_cols,
+                         int32_t *col_of_row_out /* n */, int64_t *objective_out /* 1 */,
+                         uint8_t *x_out /* n*n or NULL */, td_assign_stats *stats /* host, may be NULL */,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4  pool finder            replaces one `pool_n <pool-size> <thread> <file> <n> <out>` process
  *     (pool_n.c:209-238): findPool :153-177, drop_customers :101-151, removeDuplicates :187-207,

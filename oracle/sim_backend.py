@@ -37,7 +37,7 @@ class OracleBackend:
         mn = o["last_min"]
         return list(zip(o["rows"].tolist(), o["cols"].tolist())), (BIG_COST if mn >= BIG_COST else mn)
 
-    def solve(self, n, cost):
+    def solve(self, n, cost, n_cabs=None, n_cust=None):
         t0 = time.perf_counter()
         if n == 0:
             return []

@@ -92,6 +92,8 @@ struct AsgArgs {
     AsgCtrl *ctrl;
     int32_t *col_of_row_out; long long *objective_out; uint8_t *x_out;
     int max_phases;
+    int nr;                           // rows 0..nr-1 are real; rows nr..n-1 are constant padding rows (nr == n: balanced)
+    int32_t *col_tmp; int32_t *cost_t;   // rect with padding COLUMNS: solved on the transposed matrix
     int force_wide;                   // diagnostics / tests: always use the 64-bit relaxation
     int carry_min_levels;             // ... only after a phase of at least this many levels
     int carry_forest;                 // keep the trees that were not augmented into the next phase (see P0)
@@ -431,6 +433,8 @@ __global__ void __launch_bounds__(kAsgThreads)
 assign_kernel(AsgArgs a) {
     cg::grid_group grid = cg::this_grid();
     const int n = a.n;
+    const int nr = a.nr;              // real rows; the padding rows nr..n-1 never search, they take the leftover columns
+    const bool rect = nr < n;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -491,7 +495,8 @@ assign_kernel(AsgArgs a) {
     tick(6);
     {
         int vmn = 0;
-        for (int j = tid; j < n; j += nthreads) { const int m = a.vmin[j]; a.v[j] = m; vmn = m < vmn ? m : vmn; }
+        // rectangular instance: no column reduction -- a column that stays without a real row must keep v = 0
+        for (int j = tid; j < n; j += nthreads) { const int m = a.vmin[j]; a.v[j] = rect ? 0 : m; vmn = m < vmn ? m : vmn; }
         if (vmn < 0) atomicMax(&ctrl->cabs, (unsigned long long)(-(long long)vmn));
         for (int i = tid; i < n; i += nthreads) a.distpred[i] = kDistInf;   // per-row (minimum, argmin) keys of the next pass
     }
@@ -503,7 +508,7 @@ assign_kernel(AsgArgs a) {
     if (init_ring) {
         int nv[8], uj0 = 0;
         bool in[8];
-        ring_sweep(a.cost, n, nullptr, nullptr, n, gwarp, nwarps, lane, ring, &ctrl->ticket[1],
+        ring_sweep(a.cost, n, nullptr, nullptr, nr, gwarp, nwarps, lane, ring, &ctrl->ticket[1],
                    [&](int j0) {
                        uj0 = j0;
 #pragma unroll
@@ -525,7 +530,7 @@ assign_kernel(AsgArgs a) {
                    },
                    [&](int) {});
         grid.sync();
-        for (int i = tid; i < n; i += nthreads) {
+        for (int i = tid; i < nr; i += nthreads) {
             const unsigned long long k = a.distpred[i];
             a.u[i] = (long long)(k >> 32);
             const int j = tile_unrot(unsigned(k), row_hash(i), n);
@@ -533,7 +538,7 @@ assign_kernel(AsgArgs a) {
             atomicMin(&a.prop[j], i);
         }
     } else {
-        for (int i = gwarp; i < n; i += nwarps) {
+        for (int i = gwarp; i < nr; i += nwarps) {
             const unsigned long long k = row_min_reduced<kVec>(a, i, lane, false, 0);
             if (lane == 0) {
                 a.u[i] = (long long)(k >> 32);
@@ -551,7 +556,7 @@ assign_kernel(AsgArgs a) {
         for (int base = blockIdx.x * blockDim.x; base < n; base += nthreads) {
             const int i = base + threadIdx.x;
             bool lost = false;
-            if (i < n && a.mate_r[i] < 0) {
+            if (i < nr && a.mate_r[i] < 0) {
                 const int j = a.argcol[i];
                 if (j >= 0 && a.prop[j] == i) { a.mate_r[i] = j; a.mate_c[j] = i; }
                 else lost = true;
@@ -614,7 +619,7 @@ assign_kernel(AsgArgs a) {
                 if (j >= 0) atomicMin(&a.prop[j], i);
             }
         } else {
-            for (int i = gwarp; i < n; i += nwarps) {
+            for (int i = gwarp; i < nr; i += nwarps) {
                 if (a.mate_r[i] >= 0) continue;
                 const unsigned long long k = row_min_reduced<kVec>(a, i, lane, true, a.u[i]);
                 if (lane == 0) {
@@ -651,7 +656,7 @@ assign_kernel(AsgArgs a) {
             bool is_free = false, is_carry = false;
             if (i < n) {
                 a.claim[i] = INT_MAX;
-                is_free = a.mate_r[i] < 0;
+                is_free = i < nr && a.mate_r[i] < 0;
                 if (is_free) { a.drow[i] = 0; a.root[i] = i; }
                 else if (carried && a.drow[i] == 0) is_carry = true;
                 else a.drow[i] = kRowInf;
@@ -724,6 +729,9 @@ assign_kernel(AsgArgs a) {
         // own a sink; each of them is augmented.  Fewer phases, and a phase never scans a row twice.
         unsigned want_done = unsigned((unsigned long long)nfree * unsigned(a.deep_permille) / 1000u);
         want_done = want_done < 1u ? 1u : want_done;
+        // rectangular: stop at the first level that reaches a free column, so that every sink sits at distance D and
+        // the columns that stay unmatched keep v = 0 (their dual constraint is  v <= 0, = 0 when slack)
+        if (rect) want_done = 1u;
         tick(4);
         for (int level = 0;; ++level) {
             const int slot = level % 3;
@@ -910,6 +918,23 @@ assign_kernel(AsgArgs a) {
     }
 
     // ================= finish ===================================================================
+    if (rect) {
+        // padding rows take the columns no real row uses, in index order (any choice has the same cost)
+        if (blockIdx.x == 0 && threadIdx.x < 32) {
+            int next_row = nr;
+            for (int base = 0; base < n; base += 32) {
+                const int j = base + lane;
+                const bool is_free = j < n && a.mate_c[j] < 0;
+                const unsigned ball = __ballot_sync(0xffffffffu, is_free);
+                if (is_free) {
+                    const int r = next_row + __popc(ball & ((1u << lane) - 1));
+                    if (r < n) { a.mate_r[r] = j; a.mate_c[j] = r; }
+                }
+                next_row += __popc(ball);
+            }
+        }
+        grid.sync();
+    }
     long long part = 0;
     for (int i = tid; i < n; i += nthreads) {
         const int j = a.mate_r[i];
@@ -954,13 +979,85 @@ extern "C" size_t td_assign_workspace_bytes(int n) {
     return b;
 }
 
+namespace td {
+
+// 32 x 32 tiles through shared memory; used when the padding of a rectangular instance sits in the columns
+__global__ void asg_transpose_kernel(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n) {
+    __shared__ int32_t tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = by + r, j = bx + threadIdx.x;
+        if (i < n && j < n) tile[r][threadIdx.x] = in[size_t(i) * n + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = bx + r, j = by + threadIdx.x;
+        if (i < n && j < n) out[size_t(i) * n + j] = tile[threadIdx.x][r];
+    }
+}
+
+// row_of_col (the solution of the transposed instance) -> col_of_row and the reference's x vector
+__global__ void asg_invert_kernel(const int32_t *__restrict__ row_of_col, int n, int32_t *__restrict__ col_of_row, uint8_t *x_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int i = row_of_col[j];
+    if (i < 0 || i >= n) return;
+    col_of_row[i] = j;
+    if (x_out) x_out[size_t(i) * n + j] = 1;
+}
+
+static int assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_row_out, int64_t *objective_out, uint8_t *x_out,
+                      td_assign_stats *stats, void *workspace, size_t workspace_bytes, cudaStream_t st);
+
+}  // namespace td
+
 extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_out, int64_t *objective_out, uint8_t *x_out,
                                td_assign_stats *stats, void *workspace, size_t workspace_bytes, void *stream) {
+    return td_assign_exact_rect(cost, n, n, n, col_of_row_out, objective_out, x_out, stats, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t td_assign_rect_workspace_bytes(int n, int n_real_rows, int n_real_cols) {
+    size_t b = td_assign_workspace_bytes(n);
+    if (n > 0 && n_real_cols < n && n_real_rows == n)   // transposed copy + the row-of-column result
+        b += ((size_t(n) * n * 4 + 255) & ~size_t(255)) + ((size_t(n) * 4 + 255) & ~size_t(255));
+    return b;
+}
+
+extern "C" int td_assign_exact_rect(const int32_t *cost, int n, int n_real_rows, int n_real_cols, int32_t *col_of_row_out,
+                                    int64_t *objective_out, uint8_t *x_out, td_assign_stats *stats, void *workspace,
+                                    size_t workspace_bytes, void *stream) {
+    using namespace td;
+    if (n < 0 || n >= (1 << kRowBits)) return TD_ERR_INVALID;
+    if (n_real_rows < 0 || n_real_cols < 0 || n_real_rows > n || n_real_cols > n) return TD_ERR_INVALID;
+    if (n > 0 && n_real_rows != n && n_real_cols != n) return TD_ERR_INVALID;   // n = max(real rows, real columns)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n == 0 || n_real_cols == n)
+        return assign_run(cost, n, n_real_rows, col_of_row_out, objective_out, x_out, stats, workspace, workspace_bytes, st);
+    // padding columns: solve the transposed instance (its padding sits in the rows), then invert the matching
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (!have_device()) return TD_ERR_NO_DEVICE;
+    if (!cost || !col_of_row_out || !objective_out || !workspace) return TD_ERR_INVALID;
+    if (workspace_bytes < td_assign_rect_workspace_bytes(n, n_real_rows, n_real_cols)) return TD_ERR_WORKSPACE;
+    const size_t base_b = td_assign_workspace_bytes(n);
+    char *wsp = static_cast<char *>(workspace);
+    int32_t *cost_t = reinterpret_cast<int32_t *>(wsp + base_b);
+    int32_t *row_of_col = reinterpret_cast<int32_t *>(wsp + base_b + ((size_t(n) * n * 4 + 255) & ~size_t(255)));
+    asg_transpose_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, st>>>(cost, cost_t, n);
+    TD_LAUNCH_CHECK();
+    const int rc = assign_run(cost_t, n, n_real_cols, row_of_col, objective_out, nullptr, stats, workspace, base_b, st);
+    if (rc != TD_OK) return rc;
+    if (x_out) TD_CUDA_TRY(cudaMemsetAsync(x_out, 0, size_t(n) * n, st));
+    asg_invert_kernel<<<(n + 255) / 256, 256, 0, st>>>(row_of_col, n, col_of_row_out, x_out);
+    TD_LAUNCH_CHECK();
+    return TD_OK;
+}
+
+static int td::assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_row_out, int64_t *objective_out, uint8_t *x_out,
+                          td_assign_stats *stats, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     using namespace td;
     if (n < 0 || n >= (1 << kRowBits)) return TD_ERR_INVALID;
     if (stats) memset(stats, 0, sizeof *stats);
     if (!have_device()) return TD_ERR_NO_DEVICE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n == 0) {
         if (objective_out) TD_CUDA_TRY(cudaMemsetAsync(objective_out, 0, sizeof(int64_t), st));
         return TD_OK;
@@ -970,7 +1067,7 @@ extern "C" int td_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_o
     size_t bytes = 0;
     AsgArgs a = carve_assign(workspace, n, &bytes);
     a.cost = cost; a.n = n; a.col_of_row_out = col_of_row_out; a.objective_out = reinterpret_cast<long long *>(objective_out);
-    a.x_out = x_out; a.max_phases = n + 8;
+    a.x_out = x_out; a.max_phases = n + 8; a.nr = nr;
     a.deep_permille = 20;
     if (const char *e = getenv("TD_ASSIGN_DEEP")) a.deep_permille = atoi(e);
     if (const char *e = getenv("TD_ASSIGN_WIDE")) a.force_wide = atoi(e);

@@ -135,17 +135,23 @@ class Engine:
                 "cols": cols[:k].cpu().numpy()}
 
     # -- K2 ---------------------------------------------------------------------------------------
-    def assign(self, cost: torch.Tensor, want_x: bool = False, want_stats: bool = False):
+    def assign(self, cost: torch.Tensor, want_x: bool = False, want_stats: bool = False,
+               n_real_rows: Optional[int] = None, n_real_cols: Optional[int] = None):
+        """Exact optimum of the padded n x n matrix.  n_real_rows / n_real_cols (one of them == n) name the real block of
+        an unbalanced instance: the constant padding rows / columns are then not searched (td_assign_exact_rect); the
+        objective and the padded output layout are the same either way."""
         n = int(cost.shape[0])
+        nr = n if n_real_rows is None else int(n_real_rows)
+        nc = n if n_real_cols is None else int(n_real_cols)
         col = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
         obj = torch.zeros(1, dtype=torch.int64, device=self.device)
         x = torch.empty(n * n, dtype=torch.uint8, device=self.device) if want_x else None
-        nbytes = self.lib.td_assign_workspace_bytes(n)
+        nbytes = self.lib.td_assign_rect_workspace_bytes(n, nr, nc)
         ws = self._workspace("assign", nbytes)
         st = AssignStats() if want_stats else None
-        rc = self.lib.td_assign_exact(_ptr(cost), n, _ptr(col), _ptr(obj), _ptr(x),
-                                      ctypes.byref(st) if st is not None else None, _ptr(ws), ws.numel(), _stream())
-        check(rc, "td_assign_exact")
+        rc = self.lib.td_assign_exact_rect(_ptr(cost), n, nr, nc, _ptr(col), _ptr(obj), _ptr(x),
+                                           ctypes.byref(st) if st is not None else None, _ptr(ws), ws.numel(), _stream())
+        check(rc, "td_assign_exact_rect")
         return col[:n], obj, x, st
 
     # -- K4 ---------------------------------------------------------------------------------------
@@ -333,7 +339,9 @@ def solve_dispatch(distances, demand, cabs, fill: int = BIG_COST, cutoff: Option
     n, cost_d = _cost_device(distances, demand, cabs, fill, cutoff)
     if n == 0:
         return 0, [], 0
-    _, _, x, _ = engine().assign(cost_d, want_x=True)
+    # every real call is unbalanced (dummy rows / columns of `fill`): only the real block is searched
+    _, _, x, _ = engine().assign(cost_d, want_x=True, n_real_rows=max(len(cabs), 1) if len(cabs) < n else n,
+                                 n_real_cols=max(len(demand), 1) if len(demand) < n else n)
     return n, x.cpu().numpy(), cost_d.cpu().numpy()
 
 

@@ -83,11 +83,11 @@ class CudaBackend:
         self.times["lcm"] += time.perf_counter() - t0
         return list(zip(r["rows"].tolist(), r["cols"].tolist())), (BIG_COST if mn >= BIG_COST else mn)
 
-    def solve(self, n, cost):
+    def solve(self, n, cost, n_cabs=None, n_cust=None):
         t0 = time.perf_counter()
         if n == 0:
             return []
-        _, _, x, _ = self.eng.assign(self._device_cost(cost), want_x=True)
+        _, _, x, _ = self.eng.assign(self._device_cost(cost), want_x=True, n_real_rows=n_cabs, n_real_cols=n_cust)
         x = x.cpu().numpy()
         self.times["solve"] += time.perf_counter() - t0
         return x
@@ -338,7 +338,7 @@ class Simulator:
                 cost = self._cost(temp_demand, temp_supply)
                 line += ". Sent to solver: demand=%d, supply=%d. " % (len(temp_demand), len(temp_supply))
             self.m.max_solver_size = max(self.m.max_solver_size, len(cost))
-            x = self.backend.solve(len(cost), cost)
+            x = self.backend.solve(len(cost), cost, len(temp_supply), len(temp_demand))
             if len(cost) == 0:
                 x = []
         total = self.analyze_solution(x, cost, t, temp_demand, temp_supply)

@@ -288,6 +288,33 @@ def test_assign_is_deterministic(td):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("n_cabs,n_cust,cutoff", [(600, 218, 10), (218, 600, 10), (351, 600, None), (600, 599, None),
+                                                  (1, 40, None), (40, 1, None), (130, 257, 10), (1300, 700, 10)])
+def test_assign_unbalanced_native(td, n_cabs, n_cust, cutoff):
+    """only the real block of a padded instance is searched; objective and layout are unchanged"""
+    import torch
+    rng = np.random.default_rng(n_cabs * 1000 + n_cust)
+    dist = g.stand_distances(50)
+    n, cost = cost_ref.calculate_cost_np(dist, rng.integers(0, 50, n_cabs), rng.integers(0, 50, n_cust), cutoff=cutoff)
+    ref_obj = assign_ref.solve_scipy(cost)[0]
+    eng = td.engine()
+    c = torch.from_numpy(np.ascontiguousarray(cost, dtype=np.int32)).cuda()
+    col, obj, x, st = eng.assign(c, want_x=True, want_stats=True, n_real_rows=n_cabs if n_cabs < n else None,
+                                 n_real_cols=n_cust if n_cust < n else None)
+    col, x = col.cpu().numpy(), x.cpu().numpy()
+    assert int(obj.item()) == ref_obj
+    assert sorted(col.tolist()) == list(range(n)) and assign_ref.check_x(x, n)
+    assert int(cost[np.arange(n), col].sum()) == ref_obj
+    assert np.array_equal(np.nonzero(x.reshape(n, n))[1], col)
+    # the balanced entry point on the same matrix agrees on the objective
+    assert int(eng.assign(c)[1].item()) == ref_obj
+    # reference-shaped wrapper (split.py:139 signature) goes through the same path
+    cabs = [(i, 0, int(t)) for i, t in enumerate(rng.integers(0, 50, min(n_cabs, 64)))]
+    dem = [(i, int(f), 0) for i, f in enumerate(rng.integers(0, 50, min(n_cust, 48)))]
+    nn, xx, cc = td.solve_dispatch(dist, dem, cabs)
+    assert int((np.asarray(cc).reshape(-1) * np.asarray(xx).reshape(-1)).sum()) == assign_ref.solve_scipy(np.asarray(cc))[0]
+
+
 def test_assign_structured(td):
     rng = np.random.default_rng(77)
     for n_cabs, n_cust, S, cutoff in ((120, 200, 50, None), (200, 120, 50, 10), (218, 600, 50, 10), (600, 351, 50, 10)):
