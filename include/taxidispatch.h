@@ -234,6 +234,8 @@ int tdh_lcm(const int32_t *cost, int n, const td_lcm_params *params, int32_t *ro
             int32_t *n_pairs_out, int64_t *total_out, int32_t *last_min_out);
 int tdh_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_out, int64_t *objective_out,
                      uint8_t *x_out, td_assign_stats *stats);
+int tdh_assign_exact_rect(const int32_t *cost, int n, int n_real_rows, int n_real_cols, int32_t *col_of_row_out,
+                          int64_t *objective_out, uint8_t *x_out, td_assign_stats *stats);
 int tdh_pool_find(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
                   int shard, int n_shards, int32_t *plans_out, int32_t cap, int32_t *n_plans_out,
                   td_pool_stats *stats);

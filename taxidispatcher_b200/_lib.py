@@ -80,6 +80,7 @@ _SIGNATURES = {
     "tdh_cost_matrix": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, c_vp]),
     "tdh_lcm": (_I, [c_vp, _I, ctypes.POINTER(LcmParams), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tdh_assign_exact": (_I, [c_vp, _I, c_vp, c_vp, c_vp, ctypes.POINTER(AssignStats)]),
+    "tdh_assign_exact_rect": (_I, [c_vp, _I, _I, _I, c_vp, c_vp, c_vp, ctypes.POINTER(AssignStats)]),
     "tdh_pool_find": (_I, [c_vp, _I, c_vp, _I, _I, _I, _I, c_vp, ctypes.c_int32, c_vp, ctypes.POINTER(PoolStats)]),
     "tdh_pool_find_all": (_I, [c_vp, _I, c_vp, _I, _I, _I, c_vp, ctypes.c_int32, c_vp, ctypes.POINTER(PoolStats)]),
 }

@@ -171,24 +171,30 @@ extern "C" int tdh_lcm(const int32_t *cost, int n, const td_lcm_params *params, 
     return TD_OK;
 }
 
-extern "C" int tdh_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_out, int64_t *objective_out,
-                                uint8_t *x_out, td_assign_stats *stats) {
+extern "C" int tdh_assign_exact_rect(const int32_t *cost, int n, int n_real_rows, int n_real_cols, int32_t *col_of_row_out,
+                                     int64_t *objective_out, uint8_t *x_out, td_assign_stats *stats) {
     if (n < 0) return TD_ERR_INVALID;
     if (n == 0) { if (objective_out) *objective_out = 0; if (stats) memset(stats, 0, sizeof *stats); return TD_OK; }  // solver.py:12
     if (!cost) return TD_ERR_INVALID;
     if (!td::have_device()) return TD_ERR_NO_DEVICE;
     td::DevBuf d_cost, d_col, d_obj, d_x, d_ws;
-    const size_t wsb = td_assign_workspace_bytes(n);
+    const size_t wsb = td_assign_rect_workspace_bytes(n, n_real_rows, n_real_cols);
     TDH_TRY(d_cost.alloc(size_t(n) * n * 4)); TDH_TRY(d_col.alloc(size_t(n) * 4)); TDH_TRY(d_obj.alloc(8));
     TDH_TRY(d_ws.alloc(wsb));
     if (x_out) TDH_TRY(d_x.alloc(size_t(n) * n));
     TDH_TRY(cudaMemcpy(d_cost.p, cost, size_t(n) * n * 4, cudaMemcpyHostToDevice));
-    TDH_RC(td_assign_exact(d_cost.as<int32_t>(), n, d_col.as<int32_t>(), d_obj.as<int64_t>(),
-                           x_out ? d_x.as<uint8_t>() : nullptr, stats, d_ws.p, wsb, nullptr));
+    TDH_RC(td_assign_exact_rect(d_cost.as<int32_t>(), n, n_real_rows, n_real_cols, d_col.as<int32_t>(), d_obj.as<int64_t>(),
+                                x_out ? d_x.as<uint8_t>() : nullptr, stats, d_ws.p, wsb, nullptr));
+    TDH_TRY(cudaDeviceSynchronize());
     if (col_of_row_out) TDH_TRY(cudaMemcpy(col_of_row_out, d_col.p, size_t(n) * 4, cudaMemcpyDeviceToHost));
     if (objective_out) TDH_TRY(cudaMemcpy(objective_out, d_obj.p, 8, cudaMemcpyDeviceToHost));
     if (x_out) TDH_TRY(cudaMemcpy(x_out, d_x.p, size_t(n) * n, cudaMemcpyDeviceToHost));
     return TD_OK;
+}
+
+extern "C" int tdh_assign_exact(const int32_t *cost, int n, int32_t *col_of_row_out, int64_t *objective_out,
+                                uint8_t *x_out, td_assign_stats *stats) {
+    return tdh_assign_exact_rect(cost, n, n, n, col_of_row_out, objective_out, x_out, stats);
 }
 
 static int pool_find_retry(const int32_t *d_dem, int n, const int32_t *d_dist, int n_stands, int pool_size, int shard,

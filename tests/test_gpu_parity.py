@@ -308,6 +308,14 @@ def test_assign_unbalanced_native(td, n_cabs, n_cust, cutoff):
     assert np.array_equal(np.nonzero(x.reshape(n, n))[1], col)
     # the balanced entry point on the same matrix agrees on the objective
     assert int(eng.assign(c)[1].item()) == ref_obj
+    if n <= 300:   # host-buffer twin (what a cgo / JNI caller binds)
+        import ctypes
+        from taxidispatcher_b200 import _lib
+        hc = np.ascontiguousarray(cost, dtype=np.int32)
+        hcol, hobj = np.empty(n, np.int32), ctypes.c_int64()
+        rc = _lib.lib().tdh_assign_exact_rect(hc.ctypes.data_as(ctypes.c_void_p), n, min(n_cabs, n), min(n_cust, n),
+                                              hcol.ctypes.data_as(ctypes.c_void_p), ctypes.byref(hobj), None, None)
+        assert rc == 0 and hobj.value == ref_obj and hcol.tolist() == col.tolist()
     # reference-shaped wrapper (split.py:139 signature) goes through the same path
     cabs = [(i, 0, int(t)) for i, t in enumerate(rng.integers(0, 50, min(n_cabs, 64)))]
     dem = [(i, int(f), 0) for i, f in enumerate(rng.integers(0, 50, min(n_cust, 48)))]
