@@ -373,6 +373,8 @@ def main():
     e2e_s = float(e2e_t.item())
     if rank == 0:
         assert len(m_e2e) == 110 and st_e2e["evaluated"] == plans_per_step
+        golden_m = json.load(open(os.path.join(ROOT, "tests", "golden", "pool722.json")))["merged"]
+        assert np.asarray(m_e2e).tolist() == golden_m, "e2e pool result differs from tests/golden/pool722.json"
     h2d = dem_np.nbytes + dist_np.nbytes
     d2h = (len(my_shards) + 1) * 4 + int(110 * 36) + len(my_shards) * 32
     e2e = {"value": plans_per_step * e2e_steps / e2e_s, "unit": "plans/s", "h2d_bytes_per_step": h2d,

@@ -88,6 +88,59 @@ def gather_shard_plans(local: Sequence[Tuple[int, np.ndarray]], n: int, n_shards
     return [by_shard[s] for s in range(n_shards)]
 
 
+_SLOT_SHARD = {}
+
+
+def _find_pool_sharded_device(dem: np.ndarray, dist_table, pool_size: int, n_shards: int, rank: int, w: int, mine: List[int]):
+    """Device-resident product path (NCCL): this rank's block of shards in one asynchronous device call, the
+    survivors gathered into every rank's merge input without touching the host, merge on the device, ONE read-back.
+    Returns None (on every rank together) when some rank's record list overflowed -- the caller then takes the
+    synchronous path, which sizes the list for the next call."""
+    from . import dispatch
+    eng = dispatch.engine()
+    dev = eng.device
+    n = dem.shape[0]
+    cap = n // 2 + 1
+    slots = (n_shards + w - 1) // w
+    dem_d = dispatch._h2d_i32(dem)
+    dist_d = dispatch._h2d_i32(dist_table)
+    slot_plans = torch.zeros((slots, cap, REC_W), dtype=torch.int32, device=dev)
+    slot_counts = torch.zeros(slots, dtype=torch.int32, device=dev)
+    token = None
+    if mine:
+        _, _, token = eng.pool_find_shards(dem_d, dist_d, pool_size, mine[0], len(mine), n_shards,
+                                           out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)], defer_stats=True)
+    all_plans = torch.empty((w * slots, cap, REC_W), dtype=torch.int32, device=dev)
+    all_counts = torch.empty(w * slots, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(all_plans, slot_plans)
+    dist.all_gather_into_tensor(all_counts, slot_counts)
+    key = (w, n_shards, dev.index)
+    if key not in _SLOT_SHARD:      # logical shard of every (rank, slot); padding slots carry count 0
+        ids = []
+        for r in range(w):
+            sh = shards_for_rank(r, w, n_shards)
+            ids += sh + [0] * (slots - len(sh))
+        _SLOT_SHARD[key] = (torch.tensor(ids, dtype=torch.int32, device=dev), ids)
+    slot_shard, ids = _SLOT_SHARD[key]
+    ev = fe = 0
+    overflowed = False
+    if token is not None:
+        st, overflowed = eng.pool_read_stats(token)
+        ev, fe = sum(int(x.evaluated) for x in st), sum(int(x.feasible) for x in st)
+    t = torch.tensor([ev, fe, 1 if overflowed else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    if int(t[2]) > 0:
+        return None
+    merged, mcnt = eng.pool_merge_padded(all_plans, all_counts, slot_shard, n, pool_size)
+    counts = all_counts.cpu().numpy()
+    kept = [0] * n_shards
+    for r in range(w):
+        for k_, sh in enumerate(shards_for_rank(r, w, n_shards)):
+            kept[sh] = int(counts[r * slots + k_])
+    m = int(mcnt.item())
+    return merged[:m].cpu().numpy(), {"evaluated": int(t[0]), "feasible": int(t[1]), "kept_per_shard": kept, "kept": m}
+
+
 def find_pool_sharded(demand, dist_table, pool_size: int, n_shards: int = REF_SHARDS,
                       compute_shard: Optional[Callable] = None, merge: Optional[Callable] = None):
     """`findpool` over the ranks of the current process group: returns (merged plans, stats) on every
@@ -96,6 +149,10 @@ def find_pool_sharded(demand, dist_table, pool_size: int, n_shards: int = REF_SH
     dem = np.asarray(demand, dtype=np.int32).reshape(-1, 5)
     n = dem.shape[0]
     mine = shards_for_rank(rank, w, n_shards)
+    if compute_shard is None and merge is None and w > 1 and dist.get_backend() == "nccl" and n_shards <= 64 * w:
+        fast = _find_pool_sharded_device(dem, dist_table, pool_size, n_shards, rank, w, mine)
+        if fast is not None:
+            return fast
     if compute_shard is None:
         from . import dispatch                      # product path: one device call for the whole block
         results = dispatch.find_pool_block(dem, dist_table, pool_size, mine[0], len(mine), n_shards) if mine else []
