@@ -94,6 +94,7 @@ struct AsgArgs {
     int max_phases;
     int nr;                           // rows 0..nr-1 are real; rows nr..n-1 are constant padding rows (nr == n: balanced)
     int32_t *col_tmp; int32_t *cost_t;   // rect with padding COLUMNS: solved on the transposed matrix
+    int prof;                         // TD_ASSIGN_PROF: in-kernel timers
     int force_wide;                   // diagnostics / tests: always use the 64-bit relaxation
     int carry_min_levels;             // ... only after a phase of at least this many levels
     int carry_forest;                 // keep the trees that were not augmented into the next phase (see P0)
@@ -444,8 +445,9 @@ assign_kernel(AsgArgs a) {
     const unsigned ring = unsigned(__cvta_generic_to_shared(s_ring)) + unsigned(threadIdx.x >> 5) * (kAsgStages * kAsgStageBytes);
     AsgCtrl *ctrl = a.ctrl;
     unsigned long long t_last = 0;
+    const bool prof = a.prof != 0;   // the timers are read-modify-writes on CTA 0's path to every barrier: off by default
     auto tick = [&](int k) {   // thread 0 only: accumulate wall time since the previous tick into bucket k
-        if (tid == 0) {
+        if (prof && tid == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             if (k >= 0) ctrl->t_prof[k] += t - t_last;
@@ -788,7 +790,7 @@ assign_kernel(AsgArgs a) {
                            });
             }
             else sweep_rows<1, kVec>(a, lrows, int(fc), gwarp, nwarps, lane, bmin);
-            if (tid == 0 && narrow) ctrl->narrow_levels += 1;
+            if (prof && tid == 0 && narrow) ctrl->narrow_levels += 1;
             bmin = warp_min_u64(bmin);
             if (lane == 0) s_red[threadIdx.x >> 5] = bmin;
             __syncthreads();
@@ -797,8 +799,8 @@ assign_kernel(AsgArgs a) {
                 m = warp_min_u64(m);
                 if (threadIdx.x == 0 && m != kDistInf) atomicMin(&ctrl->gmin[slot], m >> kRowBits);
             }
-            if (tid == 0) ctrl->rows_scanned += fc;
-            if (tid == 0) {   // diagnostics: levels and scan time by frontier size (<= 32, <= 256, <= 2048, larger)
+            if (tid == 0 && fc) atomicAdd(&ctrl->rows_scanned, (unsigned long long)fc);   // fire and forget
+            if (prof && tid == 0) {   // diagnostics: levels and scan time by frontier size (<= 32, <= 256, <= 2048, larger)
                 const int bkt = fc <= 32 ? 0 : (fc <= 256 ? 1 : (fc <= 2048 ? 2 : 3));
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -860,7 +862,7 @@ assign_kernel(AsgArgs a) {
             }
             carry = warp_min_u64(carry);
             if (lane == 0 && carry != kDistInf) atomicMin(&ctrl->gmin[(level + 1) % 3], carry);
-            if (tid == 0) { ctrl->gmin[(level + 2) % 3] = kDistInf; ctrl->ticket[(level + 2) % 3] = 0; ctrl->levels += 1; }
+            if (tid == 0) { ctrl->gmin[(level + 2) % 3] = kDistInf; ctrl->ticket[(level + 2) % 3] = 0; atomicAdd(&ctrl->levels, 1u); }
             tick(2);
             grid.sync();
             tick(3);
@@ -1071,6 +1073,7 @@ static int td::assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_ro
     a.deep_permille = 20;
     if (const char *e = getenv("TD_ASSIGN_DEEP")) a.deep_permille = atoi(e);
     if (const char *e = getenv("TD_ASSIGN_WIDE")) a.force_wide = atoi(e);
+    a.prof = getenv("TD_ASSIGN_PROF") ? 1 : 0;
     a.carry_forest = 1;
     if (const char *e = getenv("TD_ASSIGN_CARRY")) a.carry_forest = atoi(e);
     a.carry_min_levels = 4;
