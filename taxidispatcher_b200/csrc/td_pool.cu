@@ -531,6 +531,21 @@ struct SelArgs {
 __device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
     return ((unsigned long long)(unsigned)r.cost << 32) | (r.rank >> 32);
 }
+// Single-level key: (cost, rank) in ONE 64-bit word, rank repacked with cb = ceil(log2 n) bits per customer.  Usable when
+// max cost < 2^(64 - 4 cb - 5) (config 3: cb = 10, costs below 2^19); it removes the second-level pass, one grid barrier
+// and the best_lo lookups from every dominance round.  Order-preserving: lexicographic (cost, p0, p1, p2, p3, perm).
+__device__ __forceinline__ unsigned long long rec_key1(const PoolRec &r, int cb) {
+    const unsigned m = (1u << kCustBits) - 1;
+    unsigned long long rk = r.rank;
+    const unsigned perm = unsigned(rk) & ((1u << kPermBits) - 1); rk >>= kPermBits;
+    const unsigned p3 = unsigned(rk) & m; rk >>= kCustBits;
+    const unsigned p2 = unsigned(rk) & m; rk >>= kCustBits;
+    const unsigned p1 = unsigned(rk) & m; rk >>= kCustBits;
+    const unsigned p0 = unsigned(rk) & m;
+    unsigned long long k = (unsigned long long)(unsigned)r.cost;
+    k = (k << cb) | p0; k = (k << cb) | p1; k = (k << cb) | p2; k = (k << cb) | p3;
+    return (k << kPermBits) | perm;
+}
 
 // Selection = the reference's sort-by-cost + greedy scan (pool_n.c:187-207), done as dominance rounds.
 // Cost is the leading key, so the scan over records with cost < t is a prefix of the whole scan:
@@ -593,6 +608,21 @@ pool_select_kernel(SelArgs a) {
     for (int i = threadIdx.x; i < a.n_slots * kMaxBands; i += blockDim.x) s_band_hi[i / kMaxBands][i % kMaxBands] = ctrl->band_hi[i / kMaxBands][i % kMaxBands];
     __syncthreads();
     auto slot_of = [&](int p0) -> int { return p0 / a.step - a.shard_begin; };
+    // single-level keys when every materialised cost fits beside the repacked rank (uniform: from the histogram)
+    int cb = 1;
+    while ((1 << cb) < n) ++cb;
+    const int cost_bits = 64 - 4 * cb - kPermBits;
+    bool single_key = cost_bits >= 1;
+    if (single_key) {
+        const int lim = cost_bits >= 31 ? kBuckets - 1 : (int)min((long long)kBuckets - 1, 1ll << cost_bits);
+        // every bucket at or above the limit (and the open-ended last bucket) must be empty
+        for (int sl = 0; sl < a.n_slots && single_key; ++sl)
+            for (int bkt = lim; bkt < kBuckets && bkt < a.cost_hi; ++bkt)
+                if (ctrl->hist[sl][bkt] != 0) { single_key = false; break; }
+        if (single_key)
+            for (int sl = 0; sl < a.n_slots && single_key; ++sl)
+                if ((kBuckets - 1) < a.cost_hi && ctrl->hist[sl][kBuckets - 1] != 0) single_key = false;
+    }
     int ts_i = 0;
     auto stamp = [&]() {
         if (tid == 0 && ts_i < 32) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ctrl->tstamp[ts_i] = t; }
@@ -692,7 +722,7 @@ pool_select_kernel(SelArgs a) {
                 for (int u = 0; u < kFiltPer; ++u) {
                     if (!live[u]) continue;
                     act[s_fbase + lrank[u]] = r[u];
-                    const unsigned long long hi = rec_hi(r[u]);
+                    const unsigned long long hi = single_key ? rec_key1(r[u], cb) : rec_hi(r[u]);
                     for (int q = 0; q < K; ++q)
                         if (hi < a.best_hi[par][p[u][q]]) atomicMin(&a.best_hi[par][p[u][q]], hi);
                 }
@@ -732,7 +762,7 @@ pool_select_kernel(SelArgs a) {
                     __syncthreads();
                     if (live) {
                         dst[s_abase + lrank] = rec;
-                        const unsigned long long hi = rec_hi(rec);
+                        const unsigned long long hi = single_key ? rec_key1(rec, cb) : rec_hi(rec);
                         for (int q = 0; q < K; ++q)
                             if (hi < a.best_hi[par][p[q]]) atomicMin(&a.best_hi[par][p[q]], hi);
                     }
@@ -743,7 +773,8 @@ pool_select_kernel(SelArgs a) {
             const unsigned n_act = ctrl->act_cnt[band][al];
             if (n_act == 0) break;
             const PoolRec *cur = a.act[al];
-            // pass B: second-level minimum among the plans that tie on the first level
+            // pass B: second-level minimum among the plans that tie on the first level (two-level keys only)
+            if (!single_key)
             for (unsigned i = tid; i < n_act; i += nthreads) {
                 const PoolRec rec = cur[i];
                 int p[4], perm;
@@ -755,7 +786,7 @@ pool_select_kernel(SelArgs a) {
                     if (a.best_hi[par][so + p[q]] == hi && lo < a.best_lo[par][so + p[q]]) atomicMin(&a.best_lo[par][so + p[q]], lo);
             }
             if (tid == 0) ctrl->act_cnt[band][al ^ 1] = 0;   // target of the next round's pass A
-            grid.sync();
+            if (!single_key) grid.sync();
             // pass C: keep the plans that hold the minimum at every one of their customers
             for (unsigned i = tid; i < n_act; i += nthreads) {
                 const PoolRec rec = cur[i];
@@ -763,10 +794,11 @@ pool_select_kernel(SelArgs a) {
                 split_rank(rec.rank, p, perm);
                 const int slot = slot_of(p[0]);
                 const int so = slot * n;
-                const unsigned long long hi = rec_hi(rec);
+                const unsigned long long hi = single_key ? rec_key1(rec, cb) : rec_hi(rec);
                 const unsigned lo = unsigned(rec.rank);
                 bool dom = true;
-                for (int q = 0; q < K; ++q) dom = dom && a.best_hi[par][so + p[q]] == hi && a.best_lo[par][so + p[q]] == lo;
+                if (single_key) { for (int q = 0; q < K; ++q) dom = dom && a.best_hi[par][so + p[q]] == hi; }
+                else for (int q = 0; q < K; ++q) dom = dom && a.best_hi[par][so + p[q]] == hi && a.best_lo[par][so + p[q]] == lo;
                 if (dom) {
                     const unsigned pos = atomicAdd(&ctrl->n_kept[slot], 1u);
                     a.kept[size_t(slot) * a.keep_cap + pos] = rec;

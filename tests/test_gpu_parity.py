@@ -193,6 +193,24 @@ def test_pool_random_tables_vs_oracle(td, k):
         assert np.array_equal(plans, oplans)
 
 
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_pool_large_costs_take_the_two_level_keys(td, k):
+    """plan costs >= 255 fall into the open-ended histogram bucket: the selection cannot pack (cost, rank) into one
+    64-bit key and uses the two-level minima; waits are long enough for the explicit slack test as well"""
+    rng = np.random.default_rng(90 + k)
+    S = 17
+    dist = rng.integers(40, 160, (S, S)).astype(np.int32)
+    np.fill_diagonal(dist, 0)
+    n = 60
+    dem = np.stack([np.arange(n), rng.integers(0, S, n), rng.integers(0, S, n), rng.integers(100, 400, n),
+                    rng.integers(50, 400, n)], axis=1).astype(np.int32)
+    for n_shards, shard in ((8, 2), (2, 1), (1, 0)):
+        plans, st = td.find_pool(dem, dist, k, shard, n_shards)
+        oplans, ost = pool_ref.find(dem, dist, k, shard, n_shards)
+        assert {q: st[q] for q in ost} == ost
+        assert np.array_equal(plans, oplans)
+
+
 def test_pool_edge_cases(td):
     dist = g.stand_distances(51)
     plans, st = td.find_pool(np.zeros((0, 5), np.int32), dist, 4, 0)
