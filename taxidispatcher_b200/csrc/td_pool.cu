@@ -575,24 +575,30 @@ pool_select_kernel(SelArgs a) {
         a.best_hi[0][c] = a.best_hi[1][c] = ~0ull;
         a.best_lo[0][c] = a.best_lo[1][c] = ~0u;
     }
-    if (tid < unsigned(a.n_slots)) {   // band bounds of this shard: cumulative histogram against 4x growing targets
-        unsigned long long cum = 0, target = kBand0;
-        unsigned in_band = 0;
-        int band = 0;
-        for (int bkt = 0; bkt < kBuckets; ++bkt) {
-            const unsigned h = bkt < a.cost_hi ? ctrl->hist[tid][bkt] : 0u;
-            cum += h; in_band += h;
-            if (band < kMaxBands - 1 && bkt < kBuckets - 1 && cum >= target) {
-                ctrl->band_hi[tid][band] = bkt + 1;
-                ctrl->band_cnt[tid][band] = in_band;
-                atomicAdd(&ctrl->band_off[band + 1], in_band);   // sizes first, prefix below
-                ++band; in_band = 0; target = cum * 4;
+    if (int(blockIdx.x) < a.n_slots) {   // band bounds of shard blockIdx.x: cumulative histogram against 4x growing targets
+        __shared__ unsigned s_hist[kBuckets];
+        const int sl = int(blockIdx.x);
+        for (int bkt = threadIdx.x; bkt < kBuckets; bkt += blockDim.x) s_hist[bkt] = bkt < a.cost_hi ? ctrl->hist[sl][bkt] : 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long cum = 0, target = kBand0;
+            unsigned in_band = 0;
+            int band = 0;
+            for (int bkt = 0; bkt < kBuckets; ++bkt) {
+                const unsigned h = s_hist[bkt];
+                cum += h; in_band += h;
+                if (band < kMaxBands - 1 && bkt < kBuckets - 1 && cum >= target) {
+                    ctrl->band_hi[sl][band] = bkt + 1;
+                    ctrl->band_cnt[sl][band] = in_band;
+                    atomicAdd(&ctrl->band_off[band + 1], in_band);   // sizes first, prefix below
+                    ++band; in_band = 0; target = cum * 4;
+                }
             }
+            ctrl->band_hi[sl][band] = INT_MAX;
+            ctrl->band_cnt[sl][band] = in_band;
+            atomicAdd(&ctrl->band_off[band + 1], in_band);
+            for (int b2 = band + 1; b2 < kMaxBands; ++b2) { ctrl->band_hi[sl][b2] = INT_MAX; ctrl->band_cnt[sl][b2] = 0; }
         }
-        ctrl->band_hi[tid][band] = INT_MAX;
-        ctrl->band_cnt[tid][band] = in_band;
-        atomicAdd(&ctrl->band_off[band + 1], in_band);
-        for (int b2 = band + 1; b2 < kMaxBands; ++b2) { ctrl->band_hi[tid][b2] = INT_MAX; ctrl->band_cnt[tid][b2] = 0; }
     }
     grid.sync();
     if (tid == 0) {
@@ -659,7 +665,15 @@ pool_select_kernel(SelArgs a) {
                 int bsel = 0;
                 while (r[u].cost >= s_band_hi[slot][bsel]) ++bsel;
                 band[u] = bsel;
-                lrank[u] = atomicAdd(&s_bcnt[bsel], 1u);
+            }
+#pragma unroll
+            for (int u = 0; u < kPartPer; ++u) {   // one shared-memory atomic per distinct band per warp
+                const unsigned peers = __match_any_sync(0xffffffffu, band[u]);
+                unsigned wbase = 0;
+                const int leader = __ffs(peers) - 1;
+                if (band[u] >= 0 && int(lane) == leader) wbase = atomicAdd(&s_bcnt[band[u]], __popc(peers));
+                wbase = __shfl_sync(0xffffffffu, wbase, leader);
+                lrank[u] = wbase + __popc(peers & ((1u << lane) - 1));
             }
             __syncthreads();
             if (threadIdx.x < kMaxBands && s_bcnt[threadIdx.x])
