@@ -78,7 +78,27 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self):
+        """In-process NVML sampling (about 200 Hz) -- an nvidia-smi subprocess takes longer than a short timed region."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+        while not self._stop.is_set():
+            r = get_reasons(h)
+            self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
+                                ["Active" if (r & b) else "Not Active" for b in bits])
+            self._stop.wait(0.005)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
