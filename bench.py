@@ -237,7 +237,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that fails between two collectives must not leave the others waiting for ever
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
     lib = _lib.lib()
     eng = dispatch.Engine()
     dev = eng.device
@@ -410,6 +412,11 @@ def main():
         except Exception as e:
             pool_large = {"error": "%s: %s" % (type(e).__name__, e)}
 
+    # ---- N > 1: independent dispatch instances, one complete 722-customer job per GPU (weak scaling view) ----
+    replicas = None
+    if world > 1 and args.components == "all":
+        replicas = run_replica_jobs(torch, dist, eng, dem_d, dist_d, world, plans_per_step, steps=min(args.steps, 30))
+
     # ---- config 5: split.py 4-way regional split of the 20k x 20k instance, ranges spread over the ranks ---
     split_comp = None
     if args.components == "all":
@@ -443,6 +450,8 @@ def main():
         components["pool_%d" % args.pool_large] = pool_large
     if split_comp is not None:
         components["split_20k_4way"] = split_comp
+    if replicas is not None:
+        components["pool_722_one_job_per_gpu"] = replicas
 
     if world > 1:
         dist.barrier()
@@ -532,6 +541,46 @@ def run_pool_large(torch, dist, np, g, eng, parallel, n_cust, rank, world, hbm_p
             "roofline": {"bound": "hbm", "achieved": per_gpu * LOGICAL_B_PER_PLAN / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": per_gpu * LOGICAL_B_PER_PLAN / 1e9 / hbm_peak,
                          "bytes_model": "logical 80 B per evaluated plan, per GPU, whole call (all passes, selection, merge)"}}
+
+
+def run_replica_jobs(torch, dist, eng, dem_d, dist_d, world, plans_per_job, steps):
+    """Batches of independent dispatch instances (north_star): every rank runs the WHOLE config-3 job (8 logical shards +
+    merge) on its own GPU, no collective on the data path.  Aggregate plans/s = world x plans per job / max-over-ranks
+    device time -- the weak-scaling companion of the headline, which splits ONE job over the ranks."""
+    dev = eng.device
+    cap = POOL_N // 2 + 1
+    plans = torch.zeros((8, cap, 9), dtype=torch.int32, device=dev)
+    counts = torch.zeros(8, dtype=torch.int32, device=dev)
+
+    def job():
+        eng.pool_find_shards(dem_d, dist_d, POOL_K, 0, 8, 8, out=plans, counts_out=counts, want_stats=False)
+        return eng.pool_merge_padded(plans, counts, None, POOL_N, POOL_K)
+
+    ok, elapsed = 1, 0.0
+    try:
+        # the first, synchronous call sizes the record list for 8 shards (asynchronous calls cannot grow it)
+        eng.pool_find_shards(dem_d, dist_d, POOL_K, 0, 8, 8, out=plans, counts_out=counts, want_stats=True)
+        for _ in range(3):
+            job()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            merged, cnt = job()
+        e1.record()
+        torch.cuda.synchronize()
+        ok = 1 if int(cnt.item()) == 110 else 0
+        elapsed = e0.elapsed_time(e1)
+    except Exception:
+        ok = 0
+    # every rank reaches the collectives whatever happened above
+    ms = torch.tensor([elapsed, float(1 - ok)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if float(ms[1]) > 0:
+        return {"error": "a replica job failed its known-answer check"}
+    per_job_ms = float(ms[0]) / steps
+    return {"jobs_per_step": world, "ms_per_step": per_job_ms, "plans_per_s": world * plans_per_job / (per_job_ms * 1e-3),
+            "scaling": "weak", "steps": steps, "l2": "not flushed between steps (inputs are 15 KB)"}
 
 
 def run_split_component(np, g, world):
