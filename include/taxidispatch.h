@@ -156,6 +156,8 @@ int td_assign_exact_rect(const int32_t *cost, int n, int n_real_rows, int n_real
  * plans_out rows use the in-memory record of pool_n.c:123-134: [p0..p{k-1}, drop-off customers
  * in drop order, zero padding, cost at column 8]; values are ROW INDICES into `demand`.
  * Survivors are written in (cost, enumeration rank) order, i.e. the order of out<thread>.csv.
+ * Limits: n <= TD_POOL_MAX_CUSTOMERS; with pool_size 4 every stand distance must be <= 2^22 (the 24 drop-off orders
+ * are evaluated in a x32 fixed point) -- larger tables return TD_ERR_INVALID (asynchronous calls: count -1).
  * ------------------------------------------------------------------------------------------ */
 typedef struct td_pool_stats {
     int64_t evaluated;  /* pool_n.c:103 count_all: leaf plans = (pickup tuple, drop-off permutation) */

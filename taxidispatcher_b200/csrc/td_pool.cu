@@ -77,6 +77,7 @@ struct PoolCtrl {
     unsigned int n_records;       // slots reserved in the record list
     unsigned int item_counter;
     unsigned int overflow;
+    unsigned int bad_input;       // K = 4: a stand distance above kDistLimit (the x32 fixed-point evaluation would overflow)
     unsigned int rounds;
     int band_hi[kMaxSlots][kMaxBands];           // exclusive cost bound of band b for each logical shard
     unsigned int band_cnt[kMaxSlots][kMaxBands]; // records of shard s in band b (from the histogram)
@@ -194,12 +195,29 @@ struct EnumArgs {
     int item_stride;              // > 1: sampling pass -- every item_stride-th item, histogram only
 };
 
-template <bool kDistSmem>
-struct DistView {
+template <bool kDistSmem, int SH>
+struct DistView {   // staged copies are pre-scaled by 2^SH; the global table is scaled at the load
     const int32_t *p; int S;
     __device__ __forceinline__ int operator()(int a, int b) const {
-        return kDistSmem ? p[a * S + b] : __ldg(p + size_t(a) * S + b);
+        return kDistSmem ? p[a * S + b] : (__ldg(p + size_t(a) * S + b) << SH);
     }
+};
+
+// customer record {from, to, thr, wait} with the detour threshold in the fixed point of the evaluation:
+// (clamped thr) * 2^SH + (2^SH - 1).  The clamp keeps every comparison exact because no ride exceeds 7 * kDistLimit.
+template <int SH>
+__device__ __forceinline__ int4 scale_cust(int4 c) {
+    if (SH > 0) {
+        const int lim = 1 << 25;
+        const int z = c.z > lim ? lim : (c.z < -lim ? -lim : c.z);
+        c.z = (z << SH) | ((1 << SH) - 1);
+    }
+    return c;
+}
+template <bool kCustSmem, int SH>
+struct CustView {
+    const int4 *p;
+    __device__ __forceinline__ int4 operator[](int i) const { return kCustSmem ? p[i] : scale_cust<SH>(p[i]); }
 };
 
 // candidates of the next pickup level from stand s with cumulative wait w: prefix length of list[s]
@@ -245,9 +263,13 @@ __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, boo
     wo.used += need;
 }
 
-// K = 4: e[i] = D(F3,T_i); t[i][j] = D(T_i,T_j); slack[i] = thr_i - (pickup legs from i to the last pickup)
-__device__ __forceinline__ void eval4(const int e[4], const int t[4][4], const int sl[4], int pick_sum, int &nfeas,
-                                      int &best) {
+// K = 4, fixed point x32: every distance is pre-multiplied by kSh4 = 32 (the tables are staged that way), the slacks are
+// 32 * slack + 31, and a leaf's key is  32 * (drop legs) + permutation index  -- ONE three-input add per leaf gives both the
+// last partial sum and the (cost, permutation) order key, and  key <= sl  is exactly  legs <= slack  because the index is
+// below 32.  e[i] = D(F3,T_i); t[i][j] = D(T_i,T_j); sl[i] from thr_i - (pickup legs from i to the last pickup).
+constexpr int kSh4 = 5;
+constexpr int kDistLimit = 1 << 22;   // 7 legs x 2^22 x 32 < 2^31
+__device__ __forceinline__ void eval4s(const int e[4], const int t[4][4], const int sl[4], int &nfeas, int &best) {
     nfeas = 0; best = INT_MAX;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -263,13 +285,12 @@ __device__ __forceinline__ void eval4(const int e[4], const int t[4][4], const i
                 if (k == i || k == j) continue;
                 const int l = 6 - i - j - k;
                 const int d2 = d1 + t[j][k];
-                const int d3 = d2 + t[k][l];
-                const bool ok = ok1 && d2 <= sl[k] && d3 <= sl[l];
                 // lexicographic permutation index (pool_n.c:137-150 order)
                 const int rj = j - (j > i);
                 const int rk = k - (k > i) - (k > j);
                 const int perm = i * 6 + rj * 2 + rk;
-                const int key = ((pick_sum + d3) << kPermBits) | perm;
+                const int key = d2 + t[k][l] + perm;
+                const bool ok = ok1 && d2 <= sl[k] && key <= sl[l];
                 nfeas += ok;
                 best = (ok && key < best) ? key : best;
             }
@@ -304,13 +325,24 @@ pool_enum_kernel(EnumArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *s_dist = reinterpret_cast<int32_t *>(smem_raw);
     int4 *s_cust = reinterpret_cast<int4 *>(smem_raw + (kDistSmem ? ((size_t(a.S) * a.S * 4 + 15) & ~size_t(15)) : 0));
-    if (kDistSmem)
-        for (int i = threadIdx.x; i < a.S * a.S; i += kEnumThreads) s_dist[i] = a.dist[i];
+    constexpr int SH = (K == 4) ? kSh4 : 0;   // fixed-point shift of the K = 4 evaluation (eval4s)
+    {
+        int dmax = 0;
+        for (int i = threadIdx.x; (kDistSmem || SH > 0) && i < a.S * a.S; i += kEnumThreads) {
+            const int v = a.dist[i];
+            dmax = v > dmax ? v : dmax;
+            if (kDistSmem) s_dist[i] = v << SH;
+        }
+        if (SH > 0 && __syncthreads_or(dmax > kDistLimit)) {   // uniform over the whole grid: every CTA scans the same table
+            if (threadIdx.x == 0) a.ctrl->bad_input = 1;
+            return;
+        }
+    }
     if (kCustSmem)
-        for (int i = threadIdx.x; i < a.n; i += kEnumThreads) s_cust[i] = a.cust[i];
+        for (int i = threadIdx.x; i < a.n; i += kEnumThreads) s_cust[i] = scale_cust<SH>(a.cust[i]);
     __syncthreads();
-    const DistView<kDistSmem> D{kDistSmem ? s_dist : a.dist, a.S};
-    const int4 *cust = kCustSmem ? s_cust : a.cust;
+    const DistView<kDistSmem, SH> D{kDistSmem ? s_dist : a.dist, a.S};
+    const CustView<kCustSmem, SH> cust{kCustSmem ? s_cust : a.cust};
     const int lane = threadIdx.x & 31;
     const int n = a.n;
     const unsigned n_items = a.ctrl->n_items;
@@ -432,7 +464,8 @@ pool_enum_kernel(EnumArgs a) {
         // threads active per instruction).  Per batch of 32 third pickups: lane l prepares candidate b2 + l (validity,
         // length n3 of its last-pickup prefix), a warp scan turns the lengths into offsets, and every lane then takes
         // flat pair indices f, f + 32, ... and finds its (third, last) by a 5-step search over the 32 offsets.
-        const int n2 = cand_count(a.cnt, c1.x, a01);
+        const int a01u = a01 >> SH;   // a01 and every D() below are in the x32 fixed point of eval4s
+        const int n2 = cand_count(a.cnt, c1.x, a01u);
         int *st_p2 = s_stage[threadIdx.x >> 5], *st_end = st_p2 + 32;
         for (int b2 = 0; b2 < n2; b2 += 32) {
             const int t2 = b2 + lane;
@@ -440,8 +473,8 @@ pool_enum_kernel(EnumArgs a) {
             if (t2 < n2) {
                 p2l = a.list[size_t(c1.x) * n + t2];
                 bool ok = p2l != p0 && p2l != p1 && (!al || al[p2l]);
-                if (ok && a01 >= kTbl) ok = a.slack[size_t(c1.x) * n + t2] >= a01;
-                if (ok) n3l = cand_count(a.cnt, cust[p2l].x, a01 + D(c1.x, cust[p2l].x));
+                if (ok && a01u >= kTbl) ok = a.slack[size_t(c1.x) * n + t2] >= a01u;
+                if (ok) n3l = cand_count(a.cnt, cust[p2l].x, (a01 + D(c1.x, cust[p2l].x)) >> SH);
                 else p2l = -1;
             }
             int incl = n3l;
@@ -459,9 +492,10 @@ pool_enum_kernel(EnumArgs a) {
             auto eval_pair = [&](bool valid, int p2, const int4 c2, int a12, int t02, int t20, int t12, int t21, int t3) {
                 int nfeas = 0, best = INT_MAX, p3 = 0;
                 const int w2 = a01 + a12;
+                const int w2u = w2 >> SH;
                 if (valid) {
                     p3 = a.list[size_t(c2.x) * n + t3];
-                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2 < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2) &&
+                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2u < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2u) &&
                             (!al || al[p3]);
                 }
                 if (valid) {
@@ -475,9 +509,10 @@ pool_enum_kernel(EnumArgs a) {
                     t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
                     t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
                     sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - w2 - a23;
-                    eval4(e, t, sl, w2 + a23, nfeas, best);
+                    eval4s(e, t, sl, nfeas, best);
                     my_eval += 24;
                     my_feas += nfeas;
+                    if (nfeas > 0) best += w2 + a23;   // pickup legs (multiples of 32): best = 32 * plan cost + permutation index
                 }
                 emit_records(a, wo, nfeas > 0, make_rank(p0, p1, p2, p3, best & 31), best >> kPermBits, lane, whist);
             };
@@ -871,7 +906,7 @@ pool_emit_kernel(const PoolRec *__restrict__ kept_all, const PoolCtrl *ctrl, int
             row[8] = me.cost;
         }
     }
-    if (threadIdx.x == 0) *n_plans_out = ctrl->overflow ? -1 : m;  // -1: record list overflowed, result invalid
+    if (threadIdx.x == 0) *n_plans_out = (ctrl->overflow || ctrl->bad_input) ? -1 : m;  // -1: record list overflowed / unsupported input
 }
 
 // ---- merge (findpool.c:83-108) ---------------------------------------------------------------
@@ -1244,6 +1279,7 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
             ++passes;
             TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
             TD_CUDA_TRY(cudaStreamSynchronize(st));
+            if (h.bad_input) return TD_ERR_INVALID;   // a stand distance above 2^22 (K = 4 fixed-point evaluation)
             double tot = 0;
             for (int sl = 0; sl < shard_count; ++sl) for (int bkt = 0; bkt < kBuckets; ++bkt) tot += h.hist[sl][bkt];
             if (tot * 64.0 * 1.3 > budget) {
@@ -1260,6 +1296,7 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
             stats_counted = true;
             TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
             TD_CUDA_TRY(cudaStreamSynchronize(st));
+            if (h.bad_input) return TD_ERR_INVALID;   // a stand distance above 2^22 (K = 4 fixed-point evaluation)
             if (!h.overflow) break;
             const int lo_b = cost_lo == INT_MIN ? 0 : (cost_lo < kBuckets ? cost_lo : kBuckets - 1);
             const int cut = cut_from_hist(lo_b, 1.0);
@@ -1313,7 +1350,7 @@ extern "C" int td_pool_read_stats(const void *workspace, int shard_count, td_poo
         stats[s].rounds = int32_t(h.total_rounds);
         stats[s].passes = 1;
     }
-    if (overflow_out) *overflow_out = h.overflow ? 1 : 0;
+    if (overflow_out) *overflow_out = (h.overflow || h.bad_input) ? 1 : 0;   // either way: repeat through the synchronous entry point
     return TD_OK;
 }
 

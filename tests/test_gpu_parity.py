@@ -211,6 +211,28 @@ def test_pool_large_costs_take_the_two_level_keys(td, k):
         assert np.array_equal(plans, oplans)
 
 
+def test_pool_k4_fixed_point_limits(td):
+    """K = 4 evaluates in a x32 fixed point: distances up to 2^22 stay exact, larger ones are refused (not clamped)"""
+    from taxidispatcher_b200 import TaxiDispatchError
+    rng = np.random.default_rng(7)
+    S, n = 9, 26
+    dist = rng.integers(1, 1 << 22, (S, S)).astype(np.int32)
+    dist[rng.integers(0, S, 6), rng.integers(0, S, 6)] = 1 << 22          # exactly the limit
+    np.fill_diagonal(dist, 0)
+    dem = np.stack([np.arange(n), rng.integers(0, S, n), rng.integers(0, S, n), rng.integers(1 << 20, 1 << 24, n),
+                    rng.integers(0, 300, n)], axis=1).astype(np.int32)
+    for k in (3, 4):
+        plans, st = td.find_pool(dem, dist, k, 0, 1)
+        oplans, ost = pool_ref.find(dem, dist, k, 0, 1)
+        assert {q: st[q] for q in ost} == ost and np.array_equal(plans, oplans)
+    dist[2, 5] = (1 << 22) + 1
+    with pytest.raises(TaxiDispatchError):
+        td.find_pool(dem, dist, 4, 0, 1)
+    plans, st = td.find_pool(dem, dist, 3, 0, 1)                           # K = 3 has no such limit
+    oplans, ost = pool_ref.find(dem, dist, 3, 0, 1)
+    assert np.array_equal(plans, oplans)
+
+
 def test_pool_edge_cases(td):
     dist = g.stand_distances(51)
     plans, st = td.find_pool(np.zeros((0, 5), np.int32), dist, 4, 0)
