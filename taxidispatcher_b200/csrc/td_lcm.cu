@@ -262,8 +262,8 @@ lcm_rounds_smem_kernel(const int32_t *__restrict__ cost, const int32_t *__restri
         if (tid == 0) s_nmine = 0;
         __syncthreads();
         // ---- stale lines: this CTA rescans those with l % G == b ----
-        for (int l = tid; l < 2 * n; l += kLcmThreads)
-            if (l % G == b && stale(l)) mine[atomicAdd(&s_nmine, 1)] = l;
+        for (int l = b + G * tid; l < 2 * n; l += G * kLcmThreads)   // the lines with l % G == b, no division
+            if (stale(l)) mine[atomicAdd(&s_nmine, 1)] = l;
         __syncthreads();
         const int nm = s_nmine;
         for (int t = warp; t < nm; t += nw) {
