@@ -59,7 +59,7 @@ constexpr int kAsgThreads = 512;
 constexpr int kRowBits = 24;                       // predecessor row in the low bits of the packed key
 constexpr unsigned long long kDistInf = ~0ull;
 constexpr long long kRowInf = (1ll << 62);
-constexpr int kGreedyRounds = 4;
+constexpr int kGreedyRounds = 8;    // upper bound; the loop stops early when a round stops paying
 
 struct AsgCtrl {
     unsigned long long gmin[3];
@@ -94,6 +94,7 @@ struct AsgArgs {
     int max_phases;
     int nr;                           // rows 0..nr-1 are real; rows nr..n-1 are constant padding rows (nr == n: balanced)
     int32_t *col_tmp; int32_t *cost_t;   // rect with padding COLUMNS: solved on the transposed matrix
+    int greedy_rounds;                // proposal rounds of the greedy initial matching
     int prof;                         // TD_ASSIGN_PROF: in-kernel timers
     int force_wide;                   // diagnostics / tests: always use the 64-bit relaxation
     int carry_min_levels;             // ... only after a phase of at least this many levels
@@ -552,6 +553,7 @@ assign_kernel(AsgArgs a) {
     }
     grid.sync();
     tick(7);
+    unsigned prev_lost = 0xffffffffu / 32u;
     for (int round = 0;; ++round) {
         // accept: the lowest proposing row takes the column; the others are listed (row, u) for the next round
         const int lst = round & 1;
@@ -577,7 +579,14 @@ assign_kernel(AsgArgs a) {
             }
         }
         grid.sync();
-        if (round == kGreedyRounds - 1) break;
+        if (round == a.greedy_rounds - 1) break;
+        if (init_ring) {   // stop early when nobody lost, or when a round matched fewer than 5 % of its losers
+            const unsigned nl = ctrl->fcount[lst];
+            if (nl == 0 || (round >= 3 && nl * 20u > prev_lost * 19u)) break;
+            prev_lost = nl;
+        } else if (round >= 3) {
+            break;   // the 64-bit fallback path rescans whole rows per loser: four rounds
+        }
         for (int j = tid; j < n; j += nthreads) a.prop[j] = INT_MAX;
         if (tid == 0) { ctrl->fcount[lst ^ 1] = 0; ctrl->ticket[lst] = 0; }
         grid.sync();
@@ -1074,6 +1083,8 @@ static int td::assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_ro
     if (const char *e = getenv("TD_ASSIGN_DEEP")) a.deep_permille = atoi(e);
     if (const char *e = getenv("TD_ASSIGN_WIDE")) a.force_wide = atoi(e);
     a.prof = getenv("TD_ASSIGN_PROF") ? 1 : 0;
+    a.greedy_rounds = kGreedyRounds;
+    if (const char *e = getenv("TD_ASSIGN_GREEDY")) { const int v = atoi(e); if (v >= 1 && v <= 64) a.greedy_rounds = v; }
     a.carry_forest = 1;
     if (const char *e = getenv("TD_ASSIGN_CARRY")) a.carry_forest = atoi(e);
     a.carry_min_levels = 4;
@@ -1110,7 +1121,7 @@ static int td::assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_ro
         stats->objective = h.objective;
         // + the two init sweeps + the strided refreshes of cached level-0 minima (one cost cell each)
         stats->rows_scanned = int64_t(h.rows_scanned) + 2 * int64_t(n) + int64_t(h.stale_cells / (unsigned long long)n);
-        stats->auction_rounds = kGreedyRounds;
+        stats->auction_rounds = a.greedy_rounds;
         stats->phases = int32_t(h.phases);
         stats->search_steps = int32_t(h.levels);
         stats->augmentations = int32_t(h.augment);
