@@ -10,7 +10,7 @@
 // on the number of distinct reduced path lengths, not on n:
 //
 //   init      v_j = min_i c_ij ; u_i = min_j (c_ij - v_j) ; greedy matching on tight cells
-//             (each row proposes a tight free column picked by a row hash, lowest row wins; 4 rounds,
+//             (each row proposes a tight free column picked by a row hash, lowest row wins; up to 8 rounds,
 //             the losers rescan only their own rows).  From here on  r_ij = c_ij - u_i - v_j >= 0
 //             and matched cells have r = 0.
 //   phase     multi-source Dijkstra from ALL free rows at once.  Costs are integers, so the
