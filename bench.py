@@ -492,9 +492,19 @@ def run_pool_large(torch, dist, np, g, eng, parallel, n_cust, rank, world, hbm_p
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     st = []
+    # record list of 1.6e9 plans = 4 x 25.6 GB of the 180 GB HBM: the ~4e10 feasible plans then need 10 cost windows
+    # instead of 40 (every window re-enumerates).  Falls back to 2e8 records if the allocation fails.
+    records = int(os.environ.get("TD_BENCH_POOL_RECORDS", "1600000000"))
     if mine:
-        _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, mine[0], len(mine), 8, max_feasible=200_000_000,
-                                        out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)])
+        try:
+            _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, mine[0], len(mine), 8, max_feasible=records,
+                                            out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)])
+        except torch.OutOfMemoryError:
+            eng._ws.pop("pool", None)
+            torch.cuda.empty_cache()
+            records = 200_000_000
+            _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, mine[0], len(mine), 8, max_feasible=records,
+                                            out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)])
     if world > 1:
         allp = torch.zeros((world * slots, cap, 9), dtype=torch.int32, device=dev)
         allc = torch.zeros(world * slots, dtype=torch.int32, device=dev)
@@ -537,7 +547,8 @@ def run_pool_large(torch, dist, np, g, eng, parallel, n_cust, rank, world, hbm_p
             ok = ok and bool((suffix + dcum[:, d] <= dist_np[F[c], T[c]] * (1 + L[c] / 100.0)).all())
     per_gpu = ev / sec / world
     return {"customers": n_cust, "seconds": sec, "plans_evaluated": ev, "feasible": fe, "merged_plans": int(len(m)),
-            "plans_per_s": ev / sec, "enumeration_passes": int(st[0].passes) if st else None, "properties_ok": bool(ok),
+            "plans_per_s": ev / sec, "enumeration_passes": int(st[0].passes) if st else None, "record_capacity": records,
+            "properties_ok": bool(ok),
             "roofline": {"bound": "hbm", "achieved": per_gpu * LOGICAL_B_PER_PLAN / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": per_gpu * LOGICAL_B_PER_PLAN / 1e9 / hbm_peak,
                          "bytes_model": "logical 80 B per evaluated plan, per GPU, whole call (all passes, selection, merge)"}}
