@@ -442,6 +442,7 @@ assign_kernel(AsgArgs a) {
     const int lane = threadIdx.x & 31;
     const int gwarp = tid >> 5, nwarps = nthreads >> 5;
     __shared__ unsigned long long s_red[kAsgThreads / 32];
+    __shared__ unsigned s_push[kAsgThreads / 32], s_push_base;
     extern __shared__ __align__(1024) unsigned char s_ring[];   // kVec only: per-warp cp.async ring
     const unsigned ring = unsigned(__cvta_generic_to_shared(s_ring)) + unsigned(threadIdx.x >> 5) * (kAsgStages * kAsgStageBytes);
     AsgCtrl *ctrl = a.ctrl;
@@ -852,9 +853,18 @@ assign_kernel(AsgArgs a) {
                 long long u_mate = 0;
                 if (now) root_p = a.root[dp_row(k)];
                 if (push) u_mate = a.u[mate];
+                // frontier slots: one global atomic per CTA and pass (up to 640 warps hit the same counter otherwise)
                 const unsigned ball = __ballot_sync(0xffffffffu, push);
-                unsigned wb = 0;
-                if (lane == 0 && ball) wb = atomicAdd(&ctrl->fcount[cur ^ 1], __popc(ball));
+                if (lane == 0) s_push[threadIdx.x >> 5] = __popc(ball);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    unsigned run = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < kAsgThreads / 32; ++w2) { const unsigned c = s_push[w2]; s_push[w2] = run; run += c; }
+                    s_push_base = run ? atomicAdd(&ctrl->fcount[cur ^ 1], run) : 0u;
+                }
+                __syncthreads();
+                unsigned wb = s_push_base + s_push[threadIdx.x >> 5];
                 if (now) a.settled[j] = 1;
                 if (sink) {
                     a.sinks[atomicAdd(&ctrl->nsinks, 1u)] = j;
@@ -862,7 +872,7 @@ assign_kernel(AsgArgs a) {
                     if (atomicMin(&a.claim[root_p], j) == INT_MAX) atomicAdd(&ctrl->ndone, 1u);
                 }
                 if (push) { a.drow[mate] = delta; a.root[mate] = root_p; }
-                wb = __shfl_sync(0xffffffffu, wb, 0);
+                __syncthreads();   // s_push is rewritten by the next pass of this loop
                 if (push) {
                     const unsigned slot_i = wb + __popc(ball & ((1u << lane) - 1));
                     a.frontier[cur ^ 1][slot_i] = mate;
@@ -1087,7 +1097,7 @@ static int td::assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_ro
     if (const char *e = getenv("TD_ASSIGN_GREEDY")) { const int v = atoi(e); if (v >= 1 && v <= 64) a.greedy_rounds = v; }
     a.carry_forest = 1;
     if (const char *e = getenv("TD_ASSIGN_CARRY")) a.carry_forest = atoi(e);
-    a.carry_min_levels = 4;
+    a.carry_min_levels = 3;
     if (const char *e = getenv("TD_ASSIGN_CARRY_MIN")) a.carry_min_levels = atoi(e);
     TD_CUDA_TRY(cudaMemsetAsync(a.ctrl, 0, sizeof(AsgCtrl), st));
     if (x_out) TD_CUDA_TRY(cudaMemsetAsync(x_out, 0, size_t(n) * n, st));
