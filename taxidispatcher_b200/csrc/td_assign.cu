@@ -75,7 +75,7 @@ struct AsgCtrl {
     unsigned int ncarry, pad4;        // rows of surviving trees that open the next phase
     unsigned int ticket[4];           // dynamic unit hand-out of the ring sweeps (slot rotates like gmin)
     unsigned int nstale, ndone;       // ndone: trees (free rows) that own a sink in the current phase
-    unsigned long long t_prof[16];     // ns spent by CTA 0 in: scan, sync, settle, sync, phase start, augment (diagnostics)
+    unsigned long long t_prof[24];     // ns spent by CTA 0 in: scan, sync, settle, sync, phase start, augment (diagnostics)
     long long objective;
     int status;
     int pad2;
@@ -692,6 +692,7 @@ assign_kernel(AsgArgs a) {
             }
         }
         grid.sync();
+        tick(16);
         const unsigned nfree = ctrl->fcount[0];
         if (first_phase && tid == 0) ctrl->free_after_init = nfree;
         first_phase = false;
@@ -705,6 +706,7 @@ assign_kernel(AsgArgs a) {
             for (int j = tid; j < n; j += nthreads)
                 if (a.mate_r[dp_row(a.base0[j])] >= 0) a.stale[atomicAdd(&ctrl->nstale, 1u)] = j;
             grid.sync();
+            tick(17);
             const unsigned ns_cols = ctrl->nstale;
             for (unsigned sidx = gwarp; sidx < ns_cols; sidx += nwarps) {
                 const int j = a.stale[sidx];
@@ -720,6 +722,7 @@ assign_kernel(AsgArgs a) {
             }
             if (tid == 0) ctrl->stale_cells += (unsigned long long)ns_cols * nfree;
             grid.sync();
+            tick(18);
             const long long sfree = ctrl->sfree;
             unsigned long long lmin = kDistInf;
             for (int j = tid; j < n; j += nthreads) {
@@ -1139,6 +1142,9 @@ static int td::assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_ro
         if (getenv("TD_ASSIGN_PROF"))
             fprintf(stderr, "[td_assign] us: scan %.0f sync1 %.0f settle %.0f sync2 %.0f phase_start %.0f augment %.0f\n",
                     h.t_prof[0] / 1e3, h.t_prof[1] / 1e3, h.t_prof[2] / 1e3, h.t_prof[3] / 1e3, h.t_prof[4] / 1e3, h.t_prof[5] / 1e3);
+        if (getenv("TD_ASSIGN_PROF"))
+            fprintf(stderr, "[td_assign] phase start us: reset + lists %.0f, stale detection %.0f, stale refresh %.0f (%.1f M cells), cache -> distances %.0f\n",
+                    h.t_prof[16] / 1e3, h.t_prof[17] / 1e3, h.t_prof[18] / 1e3, h.stale_cells / 1e6, h.t_prof[4] / 1e3);
         if (getenv("TD_ASSIGN_PROF"))
             fprintf(stderr, "[td_assign] max|c| %llu, 32-bit relaxation sweeps %llu of %u\n", h.cabs, h.narrow_levels, h.levels);
         if (getenv("TD_ASSIGN_PROF"))
