@@ -329,7 +329,8 @@ def test_assign_is_deterministic(td):
 
 
 @pytest.mark.parametrize("n_cabs,n_cust,cutoff", [(600, 218, 10), (218, 600, 10), (351, 600, None), (600, 599, None),
-                                                  (1, 40, None), (40, 1, None), (130, 257, 10), (1300, 700, 10)])
+                                                  (1, 40, None), (40, 1, None), (130, 257, 10), (1300, 700, 10),
+                                                  (0, 12, None), (12, 0, None)])
 def test_assign_unbalanced_native(td, n_cabs, n_cust, cutoff):
     """only the real block of a padded instance is searched; objective and layout are unchanged"""
     import torch
