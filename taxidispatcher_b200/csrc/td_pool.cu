@@ -267,6 +267,7 @@ __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, boo
 // 32 * slack + 31, and a leaf's key is  32 * (drop legs) + permutation index  -- ONE three-input add per leaf gives both the
 // last partial sum and the (cost, permutation) order key, and  key <= sl  is exactly  legs <= slack  because the index is
 // below 32.  e[i] = D(F3,T_i); t[i][j] = D(T_i,T_j); sl[i] from thr_i - (pickup legs from i to the last pickup).
+constexpr int kIoffSmem = 2048;    // leaders whose item offsets are staged in shared memory
 constexpr int kSh4 = 5;
 constexpr int kDistLimit = 1 << 22;   // 7 legs x 2^22 x 32 < 2^31
 __device__ __forceinline__ void eval4s(const int e[4], const int t[4][4], const int sl[4], int &nfeas, int &best) {
@@ -340,6 +341,12 @@ pool_enum_kernel(EnumArgs a) {
     }
     if (kCustSmem)
         for (int i = threadIdx.x; i < a.n; i += kEnumThreads) s_cust[i] = scale_cust<SH>(a.cust[i]);
+    // item offsets per leader: searched once per work item, so keep them next to the tables when they fit
+    __shared__ unsigned s_ioff[kIoffSmem + 1];
+    const bool ioff_smem = (a.stop - a.start) <= kIoffSmem;
+    if (ioff_smem)
+        for (int i = threadIdx.x; i <= a.stop - a.start; i += kEnumThreads) s_ioff[i] = a.item_off[i];
+    const unsigned *ioff = ioff_smem ? s_ioff : a.item_off;
     __syncthreads();
     const DistView<kDistSmem, SH> D{kDistSmem ? s_dist : a.dist, a.S};
     const CustView<kCustSmem, SH> cust{kCustSmem ? s_cust : a.cust};
@@ -379,13 +386,19 @@ pool_enum_kernel(EnumArgs a) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(&a.ctrl->item_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= (n_items + unsigned(a.item_stride) - 1) / unsigned(a.item_stride)) break;
+        // K = 4 walks the (leader, second pickup) pairs twice: first everything but the first batch of 32 third pickups,
+        // then the first batches alone.  The work is the same, but the units handed out last are at most a third of a
+        // big pair, which cuts the tail of the launch (a big pair alone runs ~0.25 ms of a 1.7 ms kernel).
+        const unsigned n_units = (K == 4) ? 2u * n_items : n_items;
+        if (item >= (n_units + unsigned(a.item_stride) - 1) / unsigned(a.item_stride)) break;
         item *= unsigned(a.item_stride);
+        const bool first_batch_only = (K == 4) && item >= n_items;
+        if (first_batch_only) item -= n_items;
         // leader = last index with item_off[idx] <= item
         int lo = 0, hi = n_lead;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (a.item_off[mid] <= item) lo = mid; else hi = mid;
+            if (ioff[mid] <= item) lo = mid; else hi = mid;
         }
         const int p0 = a.start + lo;
         const int4 c0 = cust[p0];
@@ -423,7 +436,7 @@ pool_enum_kernel(EnumArgs a) {
             continue;
         }
 
-        const int t1 = int(item - a.item_off[lo]);
+        const int t1 = int(item - ioff[lo]);
         const int p1 = a.list[size_t(c0.x) * n + t1];
         if (p1 == p0 || (al && !al[p1])) continue;
         const int4 c1 = cust[p1];
@@ -467,7 +480,7 @@ pool_enum_kernel(EnumArgs a) {
         const int a01u = a01 >> SH;   // a01 and every D() below are in the x32 fixed point of eval4s
         const int n2 = cand_count(a.cnt, c1.x, a01u);
         int *st_p2 = s_stage[threadIdx.x >> 5], *st_end = st_p2 + 32;
-        for (int b2 = 0; b2 < n2; b2 += 32) {
+        for (int b2 = first_batch_only ? 0 : 32; b2 < (first_batch_only ? (n2 < 32 ? n2 : 32) : n2); b2 += 32) {
             const int t2 = b2 + lane;
             int p2l = -1, n3l = 0;
             if (t2 < n2) {
