@@ -168,7 +168,14 @@ def reference_sample(n_slices=8, ways=64):
     return sum(counts), dt, procs
 
 
-SAMPLE_TEXT = "leading customers 0..95 of 722 (slices 0-7 of a 64-way pool_n.c shard rule, one process per slice)"
+def _host_procs():
+    """One pool_n process per host core, at most 16 (the reference fans out 8, findpool.c:138-142; more cores get more)."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
+def sample_text_64(n_slices):
+    return "leading customers 0..%d of 722 (slices 0-%d of a 64-way pool_n.c shard rule, one process per slice)" % (
+        12 * n_slices - 1, n_slices - 1)
 SAMPLE_TEXT_512 = "leading customers 0..%d of 722 (%d slices of a 512-way pool_n.c shard rule, one process per slice)"
 
 
@@ -180,7 +187,8 @@ def run_reference_arm(args, rank):
         # on 8 cores) for short runs, 1/512 slices (~0.3 s each, one per core) for long ones
         cores = os.cpu_count() or 1
         if args.steps + args.warmup <= 40:
-            ways, n_slices, sample = 64, 8, SAMPLE_TEXT
+            ways, n_slices = 64, _host_procs()
+            sample = sample_text_64(n_slices)
         else:
             ways, n_slices = 512, max(1, min(cores, 16))
             sample = SAMPLE_TEXT_512 % (2 * n_slices - 1, n_slices)
@@ -431,10 +439,11 @@ def main():
     if rank == 0 and world == 1:
         if not args.no_cpu_baseline:
             try:
-                plans, dt, procs = reference_sample()
-                plans2, dt2, _ = reference_sample()
+                n_sl = _host_procs()
+                plans, dt, procs = reference_sample(n_sl)
+                plans2, dt2, _ = reference_sample(n_sl)
                 cpu_baseline = {"value": (plans + plans2) / (dt + dt2), "unit": "plans/s", "cores": procs, "kind": "reference",
-                                "sample": SAMPLE_TEXT + ", run twice", "host_cores": os.cpu_count()}
+                                "sample": sample_text_64(n_sl) + ", run twice", "host_cores": os.cpu_count()}
             except Exception as e:
                 cpu_baseline = {"value": None, "unit": "plans/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
         if args.components == "all":
