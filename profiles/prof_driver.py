@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small, deterministic driver for ncu captures: one invocation of each hot-path kernel on its
 BASELINE.json shape.  Usage (on the GPU box, see profiles/README.md):
-    python profiles/prof_driver.py [pool] [cost] [lcm] [assign5a] [assign5b] [assign2s]
+    python profiles/prof_driver.py [pool] [pool8] [cost] [lcm] [assign5a] [assign5b] [assign2s]
 """
 import os
 import sys
@@ -22,6 +22,12 @@ if "pool" in which:
     for sh in (0, 1):
         out, cnt, st = eng.pool_find(dem, dist, 4, sh, 8)
         print("pool shard", sh, st.evaluated, st.feasible, st.kept, st.rounds)
+if "pool8" in which:   # the launch bench.py times at N = 1: all 8 logical shards in one enumeration + one selection
+    dem = torch.from_numpy(g.pool_demand()).cuda()
+    dist = torch.from_numpy(g.stand_distances(50)).cuda()
+    for _ in range(2):
+        out, cnt, st = eng.pool_find_shards(dem, dist, 4, 0, 8, 8)
+    print("pool8", sum(s.evaluated for s in st), sum(s.feasible for s in st), [int(s.kept) for s in st])
 if "cost" in which:
     cab_to, cust_from = g.config5b()
     d = torch.from_numpy(g.stand_distances(4000)).cuda()

@@ -73,18 +73,21 @@ struct PoolCtrl {
     unsigned int n_kept[kMaxSlots];
     unsigned int total_rounds;
     unsigned int n_items;         // work items of the enumeration (set once by pool_item_offsets)
+    unsigned int closure_ok;      // pool_closure_kernel: the shortest-path closure of the stand table is usable as a lower bound
+    unsigned int bad_input;       // a stand index outside the table, or (K = 4) a stand distance above kDistLimit (the x32
+                                  // fixed-point evaluation would overflow): the call reports TD_ERR_INVALID / count -1
     unsigned int pass_begin_marker;  // ---- everything below is zeroed before every enumeration pass ----
     unsigned int n_records;       // slots reserved in the record list
     unsigned int item_counter;
     unsigned int overflow;
-    unsigned int bad_input;       // K = 4: a stand distance above kDistLimit (the x32 fixed-point evaluation would overflow)
     unsigned int rounds;
     int band_hi[kMaxSlots][kMaxBands];           // exclusive cost bound of band b for each logical shard
     unsigned int band_cnt[kMaxSlots][kMaxBands]; // records of shard s in band b (from the histogram)
     unsigned int band_off[kMaxBands + 1];        // start of band b in the band-partitioned record list
     unsigned int band_cur[kMaxBands];            // write cursors of the partition pass
     unsigned int act_cnt[kMaxBands][2];          // live in-band records, ping-pong between rounds
-    unsigned int hist[kMaxSlots][kBuckets];      // records per min(cost, kBuckets-1), filled by pool_enum
+    unsigned long long hist[kMaxSlots][kBuckets];   // plans per min(cost, kBuckets-1), filled by pool_enum (64-bit: the
+                                                    // counts include plans beyond the materialised cost window)
 };
 
 __device__ __forceinline__ unsigned long long make_rank(int p0, int p1, int p2, int p3, int perm) {
@@ -104,9 +107,13 @@ __device__ __forceinline__ void split_rank(unsigned long long r, int p[4], int &
 __global__ void pool_prep_cust_kernel(const int32_t *__restrict__ demand, int n, const int32_t *__restrict__ dist,
                                       int S, int4 *cust, PoolCtrl *ctrl) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    (void)ctrl;  // zeroed by the host-side memset
     if (c >= n) return;
-    const int f = demand[c * 5 + 1], t = demand[c * 5 + 2], w = demand[c * 5 + 3], l = demand[c * 5 + 4];
+    int f = demand[c * 5 + 1], t = demand[c * 5 + 2];
+    const int w = demand[c * 5 + 3], l = demand[c * 5 + 4];
+    if (f < 0 || f >= S || t < 0 || t >= S) {   // pool_n.c:106-134 would index cost[][] out of bounds: refuse the input
+        ctrl->bad_input = 1;
+        f = 0; t = 0;
+    }
     const int d = dist[size_t(f) * S + t];
     // pool_n.c:115-116: ride > d * (1 + l/100.0), evaluated in fp64 with round-to-nearest, no contraction
     const double lim = __dmul_rn(double(d), __dadd_rn(1.0, __ddiv_rn(double(l), 100.0)));
@@ -181,9 +188,57 @@ pool_item_offsets_kernel(const int4 *__restrict__ cust, const int32_t *__restric
     for (int t = lo; t < hi; ++t) { item_off[t] = run; run += items_of(start + t); }
 }
 
+
+// Stand-table check for every pool size: a negative entry (plan costs could go negative -- a negative cost marks a hole
+// in the record list) or an entry above kDistLimit (K = 4: the x32 fixed point of eval4s needs 7 legs x 32 < 2^31; K = 2, 3:
+// the (cost << 5 | permutation) order key needs 5 legs < 2^26) is refused with TD_ERR_INVALID, never clamped.
+constexpr int kDistLimit = 1 << 22;
+__global__ void __launch_bounds__(256)
+pool_check_table_kernel(const int32_t *__restrict__ dist, long long cells, PoolCtrl *ctrl) {
+    int bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+        const int v = dist[i];
+        bad |= (v < 0) | (v > kDistLimit);
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) ctrl->bad_input = 1;
+}
+
+// Shortest-path closure D* of the stand table (Floyd-Warshall in shared memory, one CTA, S <= kPfMaxStands).
+// Every walk a -> ... -> b over the table is at least D*(a,b) long when no entry is negative, so
+//   ride(j) >= (pickup legs from j to the current last pickup) + D*(F_last, T_j)
+// at every pickup level: a pickup prefix whose bound already exceeds thr_j for one of its passengers cannot become
+// feasible whatever is picked up later and whatever the drop-off order is (pool_n.c:105-120 rejects every one of its
+// leaves, one at a time).  pool_enum<4> uses the bound to skip those leaves; they are still COUNTED (pool_n.c:103).
+// On metric tables (|i-j|, pool_n.c:179-185) D* == D.  A table with a negative entry switches the bound off.
+constexpr int kPfMaxStands = 128;
+__global__ void __launch_bounds__(1024)
+pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict__ dclose, PoolCtrl *ctrl) {
+    extern __shared__ int32_t s_d[];
+    const int cells = S * S;
+    int neg = 0;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        int v = dist[i];
+        neg |= v < 0;
+        v = v > (1 << 28) ? (1 << 28) : v;             // sums of two entries stay below 2^30
+        if (i / S == i % S) v = 0;                     // the empty walk
+        s_d[i] = v;
+    }
+    neg = __syncthreads_or(neg);
+    for (int k = 0; k < S; ++k) {
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+            const int r = i / S, c = i - r * S;
+            const int via = s_d[r * S + k] + s_d[k * S + c];   // row k and column k do not change in step k
+            if (via < s_d[i]) s_d[i] = via;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) dclose[i] = s_d[i];
+    if (threadIdx.x == 0) ctrl->closure_ok = neg ? 0u : 1u;
+}
+
 // ---- enumeration ---------------------------------------------------------------------------------
 struct EnumArgs {
-    const int4 *cust; const int32_t *dist; const int32_t *list; const int32_t *slack; const int32_t *cnt;
+    const int4 *cust; const int32_t *dist; const int32_t *dclose; const int32_t *list; const int32_t *slack; const int32_t *cnt;
     const unsigned int *item_off; PoolRec *recs; PoolCtrl *ctrl;
     int n, S, start, stop; unsigned int cap;
     int step, shard_begin;        // leader p0 belongs to call slot p0 / step - shard_begin
@@ -269,7 +324,6 @@ __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, boo
 // below 32.  e[i] = D(F3,T_i); t[i][j] = D(T_i,T_j); sl[i] from thr_i - (pickup legs from i to the last pickup).
 constexpr int kIoffSmem = 2048;    // leaders whose item offsets are staged in shared memory
 constexpr int kSh4 = 5;
-constexpr int kDistLimit = 1 << 22;   // 7 legs x 2^22 x 32 < 2^31
 __device__ __forceinline__ void eval4s(const int e[4], const int t[4][4], const int sl[4], int &nfeas, int &best) {
     nfeas = 0; best = INT_MAX;
 #pragma unroll
@@ -320,25 +374,23 @@ __device__ __forceinline__ void eval3(const int e[3], const int t[3][3], const i
     }
 }
 
-template <int K, bool kDistSmem, bool kCustSmem>
+// kPF (K = 4 with the stand table in shared memory): the closure D* is staged next to the table and the lower bound of
+// pool_closure_kernel prunes pickup prefixes at the third and at the last pickup level.
+template <int K, bool kDistSmem, bool kCustSmem, bool kPF>
 __global__ void __launch_bounds__(kEnumThreads)
 pool_enum_kernel(EnumArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t dist_b = (size_t(a.S) * a.S * 4 + 15) & ~size_t(15);
     int32_t *s_dist = reinterpret_cast<int32_t *>(smem_raw);
-    int4 *s_cust = reinterpret_cast<int4 *>(smem_raw + (kDistSmem ? ((size_t(a.S) * a.S * 4 + 15) & ~size_t(15)) : 0));
+    int32_t *s_dc = reinterpret_cast<int32_t *>(smem_raw + (kDistSmem ? dist_b : 0));
+    int4 *s_cust = reinterpret_cast<int4 *>(smem_raw + (kDistSmem ? dist_b : 0) + (kPF ? dist_b : 0));
     constexpr int SH = (K == 4) ? kSh4 : 0;   // fixed-point shift of the K = 4 evaluation (eval4s)
-    {
-        int dmax = 0;
-        for (int i = threadIdx.x; (kDistSmem || SH > 0) && i < a.S * a.S; i += kEnumThreads) {
-            const int v = a.dist[i];
-            dmax = v > dmax ? v : dmax;
-            if (kDistSmem) s_dist[i] = v << SH;
+    if (a.ctrl->bad_input) return;   // refused input (pool_prep_cust / pool_check_table): uniform, set before this launch
+    if (kDistSmem)
+        for (int i = threadIdx.x; i < a.S * a.S; i += kEnumThreads) {
+            s_dist[i] = a.dist[i] << SH;
+            if (kPF) s_dc[i] = a.dclose[i] << SH;      // D* <= D entry by entry
         }
-        if (SH > 0 && __syncthreads_or(dmax > kDistLimit)) {   // uniform over the whole grid: every CTA scans the same table
-            if (threadIdx.x == 0) a.ctrl->bad_input = 1;
-            return;
-        }
-    }
     if (kCustSmem)
         for (int i = threadIdx.x; i < a.n; i += kEnumThreads) s_cust[i] = scale_cust<SH>(a.cust[i]);
     // item offsets per leader: searched once per work item, so keep them next to the tables when they fit
@@ -349,8 +401,11 @@ pool_enum_kernel(EnumArgs a) {
     const unsigned *ioff = ioff_smem ? s_ioff : a.item_off;
     __syncthreads();
     const DistView<kDistSmem, SH> D{kDistSmem ? s_dist : a.dist, a.S};
+    const DistView<true, SH> Dc{s_dc, a.S};            // only used when kPF
     const CustView<kCustSmem, SH> cust{kCustSmem ? s_cust : a.cust};
+    const bool pf = kPF && a.ctrl->closure_ok != 0;
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1;
     const int n = a.n;
     const unsigned n_items = a.ctrl->n_items;
     const int n_lead = a.stop - a.start;
@@ -359,7 +414,11 @@ pool_enum_kernel(EnumArgs a) {
     WarpOut wo{0xffffffffu, unsigned(kChunk), false};
     __shared__ unsigned s_hist[kEnumThreads / 32][kBuckets];   // per-warp cost histogram of the warp's current shard
     unsigned *whist = s_hist[threadIdx.x >> 5];
-    __shared__ int s_stage[kEnumThreads / 32][64];                 // K = 4: third pickups and offsets of the current batch
+    // K = 4: per-warp staging of the current batch of third pickups {p2, F2, wait so far, slack of p0} / {slack of p1,
+    // slack of p2, T2, end of its last-pickup range}, and the queue of pickup tuples that passed the bound
+    __shared__ int4 s_stA[K == 4 ? kEnumThreads / 32 : 1][32];
+    __shared__ int4 s_stB[K == 4 ? kEnumThreads / 32 : 1][32];
+    __shared__ unsigned long long s_queue[K == 4 ? kEnumThreads / 32 : 1][64];
     for (int b = lane; b < kBuckets; b += 32) whist[b] = 0;
     __syncwarp();
     auto flush_counts = [&]() {
@@ -367,7 +426,7 @@ pool_enum_kernel(EnumArgs a) {
         if (cur_slot >= 0)
             for (int b = lane; b < kBuckets; b += 32) {
                 const unsigned v = whist[b];
-                if (v) { atomicAdd(&a.ctrl->hist[cur_slot][b], v); whist[b] = 0; }
+                if (v) { atomicAdd(&a.ctrl->hist[cur_slot][b], (unsigned long long)v); whist[b] = 0; }
             }
         __syncwarp();
 #pragma unroll
@@ -382,6 +441,41 @@ pool_enum_kernel(EnumArgs a) {
         my_eval = 0; my_feas = 0;
     };
 
+    // ---- K = 4: queue of surviving pickup tuples; a full batch of 32 is evaluated at a time ----------------------
+    unsigned long long *queue = s_queue[K == 4 ? (threadIdx.x >> 5) : 0];
+    int q_head = 0, q_cnt = 0;                        // warp-uniform ring state (64 entries, q_cnt < 32 between pushes)
+    constexpr unsigned kCM = (1u << kCustBits) - 1;
+    // all 24 drop-off orders of up to 32 queued tuples, one per lane; every tuple materialises its best feasible order
+    auto eval_queue = [&](int take) {
+        int nfeas = 0, best = INT_MAX;
+        unsigned long long rank = 0;
+        if (lane < take) {
+            const unsigned long long ent = queue[(q_head + lane) & 63];
+            const int q3 = int(unsigned(ent) & kCM), q2 = int(unsigned(ent >> kCustBits) & kCM);
+            const int q1 = int(unsigned(ent >> (2 * kCustBits)) & kCM), q0 = int(unsigned(ent >> (3 * kCustBits)) & kCM);
+            const int4 c0 = cust[q0], c1 = cust[q1], c2 = cust[q2], c3 = cust[q3];
+            const int a01 = D(c0.x, c1.x), a12 = D(c1.x, c2.x), a23 = D(c2.x, c3.x);
+            int e[4], t[4][4], sl[4];
+            e[0] = D(c3.x, c0.y); e[1] = D(c3.x, c1.y); e[2] = D(c3.x, c2.y); e[3] = D(c3.x, c3.y);
+            t[0][0] = t[1][1] = t[2][2] = t[3][3] = 0;
+            t[0][1] = D(c0.y, c1.y); t[1][0] = D(c1.y, c0.y);
+            t[0][2] = D(c0.y, c2.y); t[2][0] = D(c2.y, c0.y);
+            t[1][2] = D(c1.y, c2.y); t[2][1] = D(c2.y, c1.y);
+            t[0][3] = D(c0.y, c3.y); t[3][0] = D(c3.y, c0.y);
+            t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
+            t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
+            sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - a01 - a12 - a23;
+            eval4s(e, t, sl, nfeas, best);
+            my_feas += nfeas;
+            if (nfeas > 0) best += a01 + a12 + a23;   // pickup legs (multiples of 32): best = 32 * plan cost + permutation index
+            rank = make_rank(q0, q1, q2, q3, best & 31);
+        }
+        emit_records(a, wo, nfeas > 0, rank, best >> kPermBits, lane, whist);
+        q_head = (q_head + take) & 63;
+        q_cnt -= take;
+        __syncwarp();
+    };
+
     for (;;) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(&a.ctrl->item_counter, 1u);
@@ -390,20 +484,28 @@ pool_enum_kernel(EnumArgs a) {
         // then the first batches alone.  The work is the same, but the units handed out last are at most a third of a
         // big pair, which cuts the tail of the launch (a big pair alone runs ~0.25 ms of a 1.7 ms kernel).
         const unsigned n_units = (K == 4) ? 2u * n_items : n_items;
-        if (item >= (n_units + unsigned(a.item_stride) - 1) / unsigned(a.item_stride)) break;
+        const bool done = item >= (n_units + unsigned(a.item_stride) - 1) / unsigned(a.item_stride);
         item *= unsigned(a.item_stride);
         const bool first_batch_only = (K == 4) && item >= n_items;
         if (first_batch_only) item -= n_items;
-        // leader = last index with item_off[idx] <= item
-        int lo = 0, hi = n_lead;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (ioff[mid] <= item) lo = mid; else hi = mid;
+        int lo = 0;
+        if (!done) {   // leader = last index with item_off[idx] <= item
+            int hi = n_lead;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (ioff[mid] <= item) lo = mid; else hi = mid;
+            }
         }
         const int p0 = a.start + lo;
+        const int slot = done ? -2 : p0 / a.step - a.shard_begin;
+        if (slot != cur_slot) {   // the per-warp counters, histogram and tuple queue belong to one logical shard at a time
+            if (K == 4)
+                while (q_cnt > 0) eval_queue(q_cnt < 32 ? q_cnt : 32);
+            flush_counts();
+            cur_slot = slot;
+        }
+        if (done) break;
         const int4 c0 = cust[p0];
-        const int slot = p0 / a.step - a.shard_begin;
-        if (slot != cur_slot) { flush_counts(); cur_slot = slot; }
         const uint8_t *al = a.alive ? a.alive + size_t(slot) * n : nullptr;
         if (al && !al[p0]) continue;
 
@@ -441,9 +543,9 @@ pool_enum_kernel(EnumArgs a) {
         if (p1 == p0 || (al && !al[p1])) continue;
         const int4 c1 = cust[p1];
         const int a01 = D(c0.x, c1.x);  // <= W[p1] by construction of the prefix
-        const int t01 = D(c0.y, c1.y), t10 = D(c1.y, c0.y);
 
         if (K == 3) {
+            const int t01 = D(c0.y, c1.y), t10 = D(c1.y, c0.y);
             const int n2 = cand_count(a.cnt, c1.x, a01);
             for (int t2 = lane; t2 < ((n2 + 31) & ~31); t2 += 32) {
                 bool valid = t2 < n2;
@@ -472,23 +574,42 @@ pool_enum_kernel(EnumArgs a) {
             continue;
         }
 
-        // K == 4: the (third pickup, last pickup) pairs of the item are flattened over the lanes.  With lanes over the
-        // last pickup only, the candidate prefixes (a few dozen entries) left a third of the lanes idle (ncu: 22 of 32
-        // threads active per instruction).  Per batch of 32 third pickups: lane l prepares candidate b2 + l (validity,
-        // length n3 of its last-pickup prefix), a warp scan turns the lengths into offsets, and every lane then takes
-        // flat pair indices f, f + 32, ... and finds its (third, last) by a 5-step search over the 32 offsets.
-        const int a01u = a01 >> SH;   // a01 and every D() below are in the x32 fixed point of eval4s
+        // K == 4: the (third pickup, last pickup) pairs of the item are flattened over the lanes.  Per batch of 32 third
+        // pickups: lane l prepares candidate b2 + l (validity, slacks, length n3 of its last-pickup prefix, the bound at
+        // this level), a warp scan turns the lengths into offsets, and every lane then walks flat pair indices f, f + 32,
+        // ...  A pair that passes the bound is pushed on the warp's queue; whenever 32 tuples are queued they are
+        // evaluated, one per lane (all 24 drop-off orders).  a01 and every D() below are in the x32 fixed point of eval4s.
+        const int a01u = a01 >> SH;
         const int n2 = cand_count(a.cnt, c1.x, a01u);
-        int *st_p2 = s_stage[threadIdx.x >> 5], *st_end = st_p2 + 32;
+        int4 *stA = s_stA[K == 4 ? (threadIdx.x >> 5) : 0], *stB = s_stB[K == 4 ? (threadIdx.x >> 5) : 0];
+        const unsigned long long ent01 = (((unsigned long long)unsigned(p0) << kCustBits) | unsigned(p1)) << (2 * kCustBits);
+        unsigned my_tuples = 0;                        // valid pickup tuples seen by this lane (x 24 leaves each)
         for (int b2 = first_batch_only ? 0 : 32; b2 < (first_batch_only ? (n2 < 32 ? n2 : 32) : n2); b2 += 32) {
             const int t2 = b2 + lane;
-            int p2l = -1, n3l = 0;
+            int n3l = 0;
+            int4 A = make_int4(-1, 0, 0, 0), B = make_int4(0, 0, 0, 0);
             if (t2 < n2) {
-                p2l = a.list[size_t(c1.x) * n + t2];
+                const int p2l = a.list[size_t(c1.x) * n + t2];
                 bool ok = p2l != p0 && p2l != p1 && (!al || al[p2l]);
                 if (ok && a01u >= kTbl) ok = a.slack[size_t(c1.x) * n + t2] >= a01u;
-                if (ok) n3l = cand_count(a.cnt, cust[p2l].x, (a01 + D(c1.x, cust[p2l].x)) >> SH);
-                else p2l = -1;
+                if (ok) {
+                    const int4 c2 = cust[p2l];
+                    const int a12 = D(c1.x, c2.x);
+                    const int w2 = a01 + a12;
+                    n3l = cand_count(a.cnt, c2.x, w2 >> SH);
+                    A = make_int4(p2l, c2.x, w2, c0.z - w2);
+                    B = make_int4(c1.z - a12, c2.z, c2.y, 0);
+                    if (pf && (w2 >> SH) < kTbl &&
+                        !(Dc(c2.x, c0.y) <= A.w && Dc(c2.x, c1.y) <= B.x && Dc(c2.x, c2.y) <= B.y)) {
+                        // no last pickup and no drop-off order can make (p0, p1, p2) feasible.  Its leaves are counted, not
+                        // visited: the last-pickup candidates are exactly the customers with slack >= wait so far at F2
+                        // (the list prefix of length n3l), minus the three that are already on board.
+                        const int lim = 1 << 25;
+                        auto on_list = [&](const int4 c) { return (c.w < lim ? c.w : lim) * (1 << SH) - D(c2.x, c.x) >= w2 ? 1 : 0; };
+                        my_tuples += unsigned(n3l - on_list(c0) - on_list(c1) - on_list(c2));
+                        n3l = 0;
+                    }
+                }
             }
             int incl = n3l;
 #pragma unroll
@@ -497,73 +618,51 @@ pool_enum_kernel(EnumArgs a) {
                 if (lane >= o) incl += v;
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
+            B.w = incl;
             __syncwarp();
-            st_p2[lane] = p2l;
-            st_end[lane] = incl;
+            stA[lane] = A;
+            stB[lane] = B;
             __syncwarp();
-            // one (third, last) pair per lane: evaluate all 24 drop-off orders, materialise the best feasible one
-            auto eval_pair = [&](bool valid, int p2, const int4 c2, int a12, int t02, int t20, int t12, int t21, int t3) {
-                int nfeas = 0, best = INT_MAX, p3 = 0;
-                const int w2 = a01 + a12;
-                const int w2u = w2 >> SH;
-                if (valid) {
-                    p3 = a.list[size_t(c2.x) * n + t3];
-                    valid = p3 != p0 && p3 != p1 && p3 != p2 && (w2u < kTbl || a.slack[size_t(c2.x) * n + t3] >= w2u) &&
-                            (!al || al[p3]);
-                }
-                if (valid) {
-                    const int4 c3 = cust[p3];
-                    const int a23 = D(c2.x, c3.x);
-                    int e[4], t[4][4], sl[4];
-                    e[0] = D(c3.x, c0.y); e[1] = D(c3.x, c1.y); e[2] = D(c3.x, c2.y); e[3] = D(c3.x, c3.y);
-                    t[0][0] = t[1][1] = t[2][2] = t[3][3] = 0;
-                    t[0][1] = t01; t[1][0] = t10; t[0][2] = t02; t[2][0] = t20; t[1][2] = t12; t[2][1] = t21;
-                    t[0][3] = D(c0.y, c3.y); t[3][0] = D(c3.y, c0.y);
-                    t[1][3] = D(c1.y, c3.y); t[3][1] = D(c3.y, c1.y);
-                    t[2][3] = D(c2.y, c3.y); t[3][2] = D(c3.y, c2.y);
-                    sl[3] = c3.z; sl[2] = c2.z - a23; sl[1] = c1.z - a12 - a23; sl[0] = c0.z - w2 - a23;
-                    eval4s(e, t, sl, nfeas, best);
-                    my_eval += 24;
-                    my_feas += nfeas;
-                    if (nfeas > 0) best += w2 + a23;   // pickup legs (multiples of 32): best = 32 * plan cost + permutation index
-                }
-                emit_records(a, wo, nfeas > 0, make_rank(p0, p1, p2, p3, best & 31), best >> kPermBits, lane, whist);
-            };
-            const int n_valid = __popc(__ballot_sync(0xffffffffu, p2l >= 0));
-            if (total >= 96 * n_valid) {
-                // long last-pickup prefixes (thousands of customers): lanes over the last pickup keep >= 3 of 4 warps
-                // full, and the per-third-pickup lookups are done once per warp instead of once per pair
-                for (int sidx = 0; sidx < 32; ++sidx) {
-                    const int p2 = st_p2[sidx];
-                    if (p2 < 0) continue;   // warp-uniform
-                    const int n3 = st_end[sidx] - (sidx ? st_end[sidx - 1] : 0);
-                    const int4 c2 = cust[p2];
-                    const int a12 = D(c1.x, c2.x);
-                    const int t02 = D(c0.y, c2.y), t20 = D(c2.y, c0.y), t12 = D(c1.y, c2.y), t21 = D(c2.y, c1.y);
-                    for (int t3 = lane; t3 < ((n3 + 31) & ~31); t3 += 32) eval_pair(t3 < n3, p2, c2, a12, t02, t20, t12, t21, t3);
-                }
-                continue;
-            }
+            int sidx = 0, prev_end = 0;                // this lane's position in the batch: ranges are visited in order
             for (int f0 = 0; f0 < total; f0 += 32) {
                 const int f = f0 + lane;
-                const bool valid = f < total;
-                int sidx = 0;
+                bool valid = f < total;
+                int p3 = 0;
+                int4 sa = A, sb = B;
                 if (valid) {
-#pragma unroll
-                    for (int stp = 16; stp > 0; stp >>= 1)
-                        if (st_end[sidx + stp - 1] <= f) sidx += stp;
+                    int end = stB[sidx].w;
+                    while (end <= f) { prev_end = end; end = stB[++sidx].w; }
+                    sa = stA[sidx]; sb = stB[sidx];
+                    const int t3 = f - prev_end;
+                    const int w2u = sa.z >> SH;
+                    p3 = a.list[size_t(sa.y) * n + t3];
+                    valid = p3 != p0 && p3 != p1 && p3 != sa.x && (w2u < kTbl || a.slack[size_t(sa.y) * n + t3] >= w2u) &&
+                            (!al || al[p3]);
                 }
-                const int p2 = valid ? st_p2[sidx] : p0;
-                const int t3 = f - (sidx ? st_end[sidx - 1] : 0);
-                const int4 c2 = cust[p2];
-                eval_pair(valid, p2, c2, D(c1.x, c2.x), D(c0.y, c2.y), D(c2.y, c0.y), D(c1.y, c2.y), D(c2.y, c1.y), t3);
+                bool pass = valid;
+                if (valid) {
+                    ++my_tuples;
+                    if (pf) {
+                        const int4 c3 = cust[p3];
+                        const int a23 = D(sa.y, c3.x);
+                        pass = Dc(c3.x, c0.y) + a23 <= sa.w && Dc(c3.x, c1.y) + a23 <= sb.x && Dc(c3.x, sb.z) + a23 <= sb.y &&
+                               Dc(c3.x, c3.y) <= c3.z;
+                    }
+                }
+                const unsigned ball = __ballot_sync(0xffffffffu, pass);
+                if (pass)
+                    queue[(q_head + q_cnt + __popc(ball & lt_mask)) & 63] =
+                        ent01 | ((unsigned long long)unsigned(sa.x) << kCustBits) | unsigned(p3);
+                q_cnt += __popc(ball);
+                __syncwarp();
+                if (q_cnt >= 32) eval_queue(32);
             }
         }
+        my_eval += 24ull * my_tuples;
     }
-    // close the last chunk, publish the counters
+    // close the last chunk (the queue was drained and the counters published when the item loop ended)
     if (wo.base != 0xffffffffu)
         for (unsigned t = wo.used + lane; t < kChunk; t += 32) a.recs[wo.base + t].cost = -1;
-    flush_counts();
 }
 
 // ---- selection -----------------------------------------------------------------------------------
@@ -615,6 +714,10 @@ pool_select_kernel(SelArgs a) {
     const int K = a.K;
     const int n = a.n;
     PoolCtrl *ctrl = a.ctrl;
+    // The record list overflowed (asynchronous single pass) or the input was refused: the histogram kept counting, so the
+    // band sizes exceed what was materialised -- nothing below may run.  Both flags are final when the enumeration has
+    // ended, every thread of the grid sees the same values and leaves before the first barrier; pool_emit reports -1.
+    if (ctrl->overflow || ctrl->bad_input) return;
     if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ctrl->tstamp[31] = t; }
     __shared__ int s_band_hi[kMaxSlots][kMaxBands];
     const unsigned n_state = unsigned(n) * unsigned(a.n_slots);
@@ -626,7 +729,7 @@ pool_select_kernel(SelArgs a) {
     if (int(blockIdx.x) < a.n_slots) {   // band bounds of shard blockIdx.x: cumulative histogram against 4x growing targets
         __shared__ unsigned s_hist[kBuckets];
         const int sl = int(blockIdx.x);
-        for (int bkt = threadIdx.x; bkt < kBuckets; bkt += blockDim.x) s_hist[bkt] = bkt < a.cost_hi ? ctrl->hist[sl][bkt] : 0u;
+        for (int bkt = threadIdx.x; bkt < kBuckets; bkt += blockDim.x) s_hist[bkt] = bkt < a.cost_hi ? unsigned(ctrl->hist[sl][bkt]) : 0u;   // materialised records: < 2^32
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long cum = 0, target = kBand0;
@@ -1068,7 +1171,7 @@ pool_pairs_enum_kernel(const int32_t *__restrict__ from, const int32_t *__restri
     }
     __syncthreads();
     for (int b = threadIdx.x; b < kBuckets; b += blockDim.x)
-        if (s_hist[b]) atomicAdd(&ctrl->hist[0][b], s_hist[b]);
+        if (s_hist[b]) atomicAdd(&ctrl->hist[0][b], (unsigned long long)s_hist[b]);
     if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->n_records = unsigned(total);
 }
 
@@ -1095,7 +1198,7 @@ pool_pairs_emit_kernel(const PoolRec *__restrict__ kept, const PoolCtrl *ctrl, i
 }
 
 struct PoolWorkspace {
-    int4 *cust; int32_t *list, *slack, *cnt; unsigned int *item_off; PoolRec *recs[2]; PoolRec *act[2]; PoolRec *kept;
+    int4 *cust; int32_t *list, *slack, *cnt, *dclose; unsigned int *item_off; PoolRec *recs[2]; PoolRec *act[2]; PoolRec *kept;
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolCtrl *ctrl; size_t bytes;
 };
 
@@ -1109,6 +1212,7 @@ static PoolWorkspace carve_pool(void *ws, int n, int S, int n_slots, int64_t max
     w.list = c.take<int32_t>(size_t(S) * nn);
     w.slack = c.take<int32_t>(size_t(S) * nn);
     w.cnt = c.take<int32_t>(size_t(S) * kTbl);
+    w.dclose = c.take<int32_t>(S <= kPfMaxStands ? size_t(S) * S : 1);
     w.item_off = c.take<unsigned int>(nn + 2);
     w.recs[0] = c.take<PoolRec>(size_t(max_records));
     w.recs[1] = c.take<PoolRec>(size_t(max_records));
@@ -1134,22 +1238,27 @@ static int64_t record_slack() { return int64_t(kChunk) * 148 * 64; }
     } while (0)
 
 template <int K>
-static int launch_enum(const EnumArgs &a, int grid, cudaStream_t st) {
+static int launch_enum(const EnumArgs &a, int sms, bool closure, cudaStream_t st) {
     const size_t dist_b = (size_t(a.S) * a.S * 4 + 15) & ~size_t(15);
     const size_t cust_b = size_t(a.n) * 16;
     const bool ds = dist_b <= 64 * 1024;
-    const bool cs = cust_b <= 96 * 1024;
-    const size_t smem = (ds ? dist_b : 0) + (cs ? cust_b : 0);
-#define TD_ENUM_CASE(DS, CS)                                                                                             \
+    const bool pf = K == 4 && ds && closure;          // the closure table is staged next to the distance table
+    const bool cs = cust_b <= (pf && dist_b > 32 * 1024 ? 48 * 1024 : 96 * 1024);
+    const size_t smem = (ds ? dist_b : 0) + (pf ? dist_b : 0) + (cs ? cust_b : 0);
+#define TD_ENUM_CASE(DS, CS, PF)                                                                                         \
     do {                                                                                                                 \
-        TD_CUDA_TRY(cudaFuncSetAttribute(pool_enum_kernel<K, DS, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                         int(200 * 1024)));                                                              \
-        pool_enum_kernel<K, DS, CS><<<grid, kEnumThreads, smem, st>>>(a);                                                \
-    } while (0)
-    if (ds && cs) TD_ENUM_CASE(true, true);
-    else if (ds) TD_ENUM_CASE(true, false);
-    else if (cs) TD_ENUM_CASE(false, true);
-    else TD_ENUM_CASE(false, false);
+        auto kern = pool_enum_kernel<K, DS, CS, PF>;                                                                     \
+        TD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(190 * 1024)));           \
+        int per_sm = 0;                                                                                                  \
+        TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEnumThreads, smem));                   \
+        if (per_sm < 1) return TD_ERR_CUDA;                                                                              \
+        kern<<<sms * (per_sm > 4 ? 4 : per_sm), kEnumThreads, smem, st>>>(a);   /* resident CTAs only: a CTA that    */ \
+    } while (0)                                                                  /* starts late finds the queue empty */
+    if (pf) { if (cs) TD_ENUM_CASE(true, true, (K == 4)); else TD_ENUM_CASE(true, false, (K == 4)); }
+    else if (ds && cs) TD_ENUM_CASE(true, true, false);
+    else if (ds) TD_ENUM_CASE(true, false, false);
+    else if (cs) TD_ENUM_CASE(false, true, false);
+    else TD_ENUM_CASE(false, false, false);
 #undef TD_ENUM_CASE
     TD_LAUNCH_CHECK();
     return TD_OK;
@@ -1203,6 +1312,20 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
     TD_LAUNCH_CHECK();
     pool_item_offsets_kernel<<<1, 1024, 0, st>>>(w.cust, w.cnt, start, stop, pool_size, w.item_off, w.ctrl);
     TD_LAUNCH_CHECK();
+    {
+        const long long cells = (long long)n_stands * n_stands;
+        const long long want = (cells + 256 * 16 - 1) / (256 * 16);
+        const int grid = int(want < 1 ? 1 : (want > 4LL * device_sm_count() ? 4LL * device_sm_count() : want));
+        pool_check_table_kernel<<<grid, 256, 0, st>>>(dist, cells, w.ctrl);
+        TD_LAUNCH_CHECK();
+    }
+    const bool closure = pool_size == 4 && n_stands <= kPfMaxStands;
+    if (closure) {
+        const size_t cl_smem = size_t(n_stands) * n_stands * 4;
+        TD_CUDA_TRY(cudaFuncSetAttribute(pool_closure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(64 * 1024)));
+        pool_closure_kernel<<<1, 1024, cl_smem, st>>>(dist, n_stands, w.dclose, w.ctrl);
+        TD_LAUNCH_CHECK();
+    }
 
     const int sms = device_sm_count();
     int sel_per_sm = 0;
@@ -1220,14 +1343,14 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
     };
     auto run_enum = [&](int cost_lo, int cost_hi, bool use_alive, bool count_stats, int stride) -> int {
         EnumArgs ea;
-        ea.cust = w.cust; ea.dist = dist; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
+        ea.cust = w.cust; ea.dist = dist; ea.dclose = w.dclose; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
         ea.recs = w.recs[0]; ea.ctrl = w.ctrl; ea.n = n; ea.S = n_stands; ea.start = start; ea.stop = stop;
         ea.cap = unsigned(rec_cap64); ea.step = step; ea.shard_begin = shard_begin;
         ea.cost_lo = cost_lo; ea.cost_hi = cost_hi; ea.alive = use_alive ? w.alive : nullptr;
         ea.count_stats = count_stats ? 1 : 0; ea.item_stride = stride;
         ProfScope prof(TD_PROF_POOL_ENUM, st);
-        return pool_size == 4 ? launch_enum<4>(ea, sms * 4, st) : pool_size == 3 ? launch_enum<3>(ea, sms * 4, st)
-                                                                                   : launch_enum<2>(ea, sms * 4, st);
+        return pool_size == 4 ? launch_enum<4>(ea, sms, closure, st) : pool_size == 3 ? launch_enum<3>(ea, sms, false, st)
+                                                                                        : launch_enum<2>(ea, sms, false, st);
     };
     auto run_select = [&](bool first, int window_hi) -> int {
         SelArgs sa;

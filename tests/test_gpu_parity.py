@@ -226,11 +226,20 @@ def test_pool_k4_fixed_point_limits(td):
         oplans, ost = pool_ref.find(dem, dist, k, 0, 1)
         assert {q: st[q] for q in ost} == ost and np.array_equal(plans, oplans)
     dist[2, 5] = (1 << 22) + 1
+    for k in (2, 3, 4):                                                    # K = 2, 3: the (cost << 5 | perm) key has the same limit
+        with pytest.raises(TaxiDispatchError):
+            td.find_pool(dem, dist, k, 0, 1)
+    dist[2, 5] = -1                                                        # a negative cost would mark a hole in the record list
     with pytest.raises(TaxiDispatchError):
         td.find_pool(dem, dist, 4, 0, 1)
-    plans, st = td.find_pool(dem, dist, 3, 0, 1)                           # K = 3 has no such limit
-    oplans, ost = pool_ref.find(dem, dist, 3, 0, 1)
-    assert np.array_equal(plans, oplans)
+    dist[2, 5] = 3
+    dem[7, 1] = S                                                          # stand index outside the table (pool_n.c would read out of bounds)
+    with pytest.raises(TaxiDispatchError):
+        td.find_pool(dem, dist, 4, 0, 1)
+    dem[7, 1] = 0
+    dem[3, 2] = -1
+    with pytest.raises(TaxiDispatchError):
+        td.find_pool(dem, dist, 3, 0, 1)
 
 
 def test_pool_edge_cases(td):
