@@ -209,6 +209,8 @@ int td_pool_pairs(const int32_t *from, const int32_t *to, int n, const int32_t *
  * which falls back to cost windows. */
 int td_pool_read_stats(const void *workspace, int shard_count, td_pool_stats *stats /* host[shard_count] */,
                        int *overflow_out /* host, may be NULL */, void *stream);
+/* bytes td_pool_read_stats copies device -> host (for callers that account their PCIe traffic) */
+size_t td_pool_read_stats_bytes(void);
 
 /* findpool.c:83-108: concatenated shard survivors (shard order) -> sort on column 8 -> greedy
  * disjoint scan.  Reference quirk kept: for pool_size < 4 findpool.c sorts on a column it never

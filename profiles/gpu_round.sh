@@ -12,8 +12,8 @@ for w in $what; do
     ncu_list) B="python bench.py --steps 2 --warmup 3 --components none --no-cpu-baseline"
        timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${tag}_launches_bench.csv $B > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu_list rc=$?";;
     ncu_full) timeout 300 python profiles/prof_driver.py pool8 > gpurun_out/${tag}_plain_driver.log 2>&1 && \
-       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pool_enum|pool_select" -c 6 -o gpurun_out/${tag}_prof -f \
+       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pool_enum|pool_select" -c 16 -o gpurun_out/${tag}_prof -f \
          python profiles/prof_driver.py pool8 > gpurun_out/${tag}_ncu_driver.log 2>&1; echo "ncu_full rc=$?";;
-    sanitize) timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "pool_small or pool_random or pool_edge or pool_k4" > gpurun_out/${tag}_sanitize.log 2>&1; echo "sanitize rc=$?"; tail -5 gpurun_out/${tag}_sanitize.log;;
+    ts) timeout 300 python profiles/pool_ts.py > gpurun_out/${tag}_ts.log 2>&1; echo "ts rc=$?"; cat gpurun_out/${tag}_ts.log;;
   esac
 done

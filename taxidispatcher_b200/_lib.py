@@ -74,6 +74,7 @@ _SIGNATURES = {
     "td_pool_pairs_workspace_bytes": (ctypes.c_size_t, [_I]),
     "td_pool_pairs": (_I, [c_vp, c_vp, _I, c_vp, _I, _I, ctypes.c_double, c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "td_pool_read_stats": (_I, [c_vp, _I, ctypes.POINTER(PoolStats), ctypes.POINTER(ctypes.c_int), c_vp]),
+    "td_pool_read_stats_bytes": (ctypes.c_size_t, []),
     "td_pool_merge_workspace_bytes": (ctypes.c_size_t, [_I, _I]),
     "td_pool_merge": (_I, [c_vp, _I, _I, _I, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "td_pool_merge_padded": (_I, [c_vp, c_vp, c_vp, _I, _I, _I, _I, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),

@@ -1468,6 +1468,8 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
     return over_cap ? TD_ERR_CAPACITY : TD_OK;
 }
 
+extern "C" size_t td_pool_read_stats_bytes(void) { return offsetof(td::PoolCtrl, rounds) + sizeof(unsigned int); }
+
 extern "C" int td_pool_read_stats(const void *workspace, int shard_count, td_pool_stats *stats, int *overflow_out,
                                   void *stream) {
     using namespace td;

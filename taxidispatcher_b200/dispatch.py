@@ -47,12 +47,26 @@ def _stream():
 
 
 _PINNED = {}   # numel -> reusable pinned staging buffer (cudaHostAlloc per call costs more than small copies)
+COPIED = {"h2d": 0, "d2h": 0}   # bytes the host-facing functions moved over PCIe so far (bench.py reports the per-call difference)
+
+
+def _d2h(t: torch.Tensor) -> np.ndarray:
+    """Device tensor -> numpy, counted."""
+    arr = t.cpu().numpy()
+    COPIED["d2h"] += arr.nbytes
+    return arr
+
+
+def _d2h_int(t: torch.Tensor) -> int:
+    COPIED["d2h"] += t.element_size()
+    return int(t.item())
 
 
 def _h2d_i32(a, pinned: bool = True) -> torch.Tensor:
     """Host array-like -> int32 CUDA tensor through pinned staging (asynchronous copy on the current stream).
     Staging buffers are reused; the stream is synchronised before a buffer is overwritten again."""
     arr = np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+    COPIED["h2d"] += arr.nbytes
     if not pinned or arr.size == 0:
         return torch.from_numpy(arr).to("cuda")
     if arr.size > (1 << 22):                       # big matrices: one-off pinned copy
@@ -230,6 +244,7 @@ class Engine:
         st = (PoolStats * shard_count)()
         ov = ctypes.c_int(0)
         check(self.lib.td_pool_read_stats(_ptr(ws), shard_count, st, ctypes.byref(ov), _stream()), "td_pool_read_stats")
+        COPIED["d2h"] += int(self.lib.td_pool_read_stats_bytes())
         return list(st), bool(ov.value)
 
     def pool_pairs(self, frm: torch.Tensor, to: torch.Tensor, dist: torch.Tensor, accept_all: bool = True,
@@ -454,10 +469,10 @@ def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
         merged, mcnt = eng.pool_merge_padded(out, cnt, None, n, pool_size)
         st, overflowed = eng.pool_read_stats(token)
         if not overflowed:
-            m = int(mcnt.item())
+            m = _d2h_int(mcnt)
             stats.update(evaluated=sum(int(s.evaluated) for s in st), feasible=sum(int(s.feasible) for s in st),
                          rounds=int(st[0].rounds), kept_per_shard=[int(s.kept) for s in st], kept=m)
-            return merged[:m].cpu().numpy(), stats
+            return _d2h(merged[:m]), stats
         eng._ws[fast_key] = False                         # input outgrew the record list: cost windows below
     parts, counts = [], []
     single = True
@@ -476,6 +491,6 @@ def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
     slot_plans = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
     slot_counts = counts[0] if len(counts) == 1 else torch.cat(counts, dim=0)
     merged, cnt = eng.pool_merge_padded(slot_plans, slot_counts, None, n, pool_size)
-    m = int(cnt.item())
+    m = _d2h_int(cnt)
     stats["kept"] = m
-    return merged[:m].cpu().numpy(), stats
+    return _d2h(merged[:m]), stats

@@ -128,17 +128,19 @@ def _find_pool_sharded_device(dem: np.ndarray, dist_table, pool_size: int, n_sha
         st, overflowed = eng.pool_read_stats(token)
         ev, fe = sum(int(x.evaluated) for x in st), sum(int(x.feasible) for x in st)
     t = torch.tensor([ev, fe, 1 if overflowed else 0], dtype=torch.int64, device=dev)
+    dispatch.COPIED["h2d"] += 24
     dist.all_reduce(t)
-    if int(t[2]) > 0:
+    t_h = dispatch._d2h(t)
+    if int(t_h[2]) > 0:
         return None
     merged, mcnt = eng.pool_merge_padded(all_plans, all_counts, slot_shard, n, pool_size)
-    counts = all_counts.cpu().numpy()
+    counts = dispatch._d2h(all_counts)
     kept = [0] * n_shards
     for r in range(w):
         for k_, sh in enumerate(shards_for_rank(r, w, n_shards)):
             kept[sh] = int(counts[r * slots + k_])
-    m = int(mcnt.item())
-    return merged[:m].cpu().numpy(), {"evaluated": int(t[0]), "feasible": int(t[1]), "kept_per_shard": kept, "kept": m}
+    m = dispatch._d2h_int(mcnt)
+    return dispatch._d2h(merged[:m]), {"evaluated": int(t_h[0]), "feasible": int(t_h[1]), "kept_per_shard": kept, "kept": m}
 
 
 def find_pool_sharded(demand, dist_table, pool_size: int, n_shards: int = REF_SHARDS,

@@ -56,11 +56,50 @@ def pool_case(dem, k, label):
             "merged": merged.tolist()}
 
 
+def _huge_slice(args):
+    """One `pool_n_huge512 4 t demand.csv n out.csv` run of the compiled reference (pool_n.c:209-238)."""
+    import re
+    import subprocess
+    import tempfile
+    exe, dem, t = args
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "demand.csv"), "w") as f:
+            f.write(g.demand_csv(dem))
+        res = subprocess.run([exe, "4", str(t), "demand.csv", str(len(dem)), "out.csv"], cwd=td, capture_output=True,
+                             text=True, check=True)
+        plans = pool_ref.parse_result_csv(open(os.path.join(td, "out.csv")).read(), 4)
+    m = {k: int(v) for k, v in re.findall(r"(Count ALL|Count|Not duplicated count): (-?\d+)", res.stdout)}
+    return {"slice": t, "plans": plans.tolist(),
+            "stats": {"evaluated_mod_2_32": m["Count ALL"] % (1 << 32), "feasible": m["Count"], "kept": m["Not duplicated count"]}}
+
+
+def large_slices(spec):
+    """north star (>= 5k customers): slices of the reference's own shard rule with MAX_THREAD = 512 (pool_n.c:13,226-229)
+    -- the rule is the same for any thread count, so `find_pool(dem, dist, 4, shard=t, n_shards=512)` must reproduce
+    each slice bit for bit.  count_all is a 32-bit int in the reference (pool_n.c:28): compared modulo 2^32."""
+    import subprocess
+    n, ts = spec.split(":")
+    n = int(n)
+    ts = [int(t) for t in ts.split(",")]
+    exe = os.path.join(ROOT, "oracle", "_ref", "pool_n_huge512")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/pool_n_huge512"])
+    dem = g.pool_demand(n, seed=n)
+    with cf.ProcessPoolExecutor(min(len(ts), 6)) as ex:
+        slices = list(ex.map(_huge_slice, [(exe, dem, t) for t in ts]))
+    dump("pool%d_slices.json" % n, {"label": "large_%d_512way" % n, "pool_size": 4, "n": n, "n_stands": 50, "seed": n,
+                                    "n_shards": 512, "demand_sha256": sha(dem), "slices": slices})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-722", action="store_true")
     ap.add_argument("--only-large", type=int, default=0, help="only write pool<N>.json for N customers (minutes of CPU)")
+    ap.add_argument("--large-slices", default="", help="N:t0,t1,...: slices t of the 512-way shard rule of pool_n.c for N "
+                                                        "customers (north-star size; ~10 CPU-minutes per slice, run in parallel)")
     a = ap.parse_args()
+    if a.large_slices:
+        large_slices(a.large_slices)
+        return
     if a.only_large:
         dem = g.pool_demand(a.only_large, seed=a.only_large)
         c = pool_case(dem, 4, "large_%d" % a.only_large)

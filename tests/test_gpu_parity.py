@@ -391,6 +391,30 @@ def test_assign_config2_and_mid_sizes(td):
     _check_assign(td, g.config5b_cost(5000), gold["config5b_n5000"]["objective"])
 
 
+def test_assign_20k_north_star_objectives(td):
+    """north star: exact optimum of 20 000 x 20 000.  For costs |a_i - b_j| the sorted matching is optimal (exchange
+    argument), so the optimum of config 5-B is sum |sort(cab_to) - sort(cust_from)|; on config 5-A (U[1,39]) every row
+    holds a 1 and the optimum reaches the lower bound n * 1 (checked as equality with the bound)."""
+    import torch
+    cab_to, cust_from = g.config5b()
+    closed = int(np.abs(np.sort(cab_to).astype(np.int64) - np.sort(cust_from).astype(np.int64)).sum())
+    assert closed == 480177
+    eng = td.engine()
+    a = torch.from_numpy(cab_to).cuda().to(torch.int32)
+    b = torch.from_numpy(cust_from).cuda().to(torch.int32)
+    cost = (a[:, None] - b[None, :]).abs().contiguous()
+    col, obj, _, st = eng.assign(cost, want_stats=True)
+    col_h = col.cpu().numpy().astype(np.int64)
+    assert sorted(col_h.tolist()) == list(range(20000))
+    assert int(obj.item()) == closed == int(np.abs(cab_to.astype(np.int64) - cust_from[col_h]).sum())
+    del cost
+    c5a = torch.from_numpy(g.config5a()).cuda()
+    col, obj, _, _ = eng.assign(c5a)
+    col_h = col.cpu().numpy().astype(np.int64)
+    assert sorted(col_h.tolist()) == list(range(20000))
+    assert int(obj.item()) == 20000 == int(c5a.cpu().numpy()[np.arange(20000), col_h].sum())
+
+
 def test_assign_optimum_not_above_lcm(td):
     """heuristic.py:40's invariant: the optimum never exceeds the LCM total"""
     C = g.config2()[:400, :400].copy()
@@ -499,6 +523,49 @@ def test_pool_1200_customers_golden_single_pass_and_windows(td):
         merged, mc = eng.pool_merge_padded(out, cnt, None, 1200, 4)
         assert merged[: int(mc.item())].cpu().numpy().tolist() == gold["merged"]
     assert st[0].passes > 1
+
+
+def test_pool_async_overflow_reports_minus_one_and_recovers(td):
+    """The asynchronous single pass (stats == NULL) cannot fall back to cost windows: when the record list is too small
+    every count comes back as -1, nothing is read or written out of bounds (the selection does not run), and the
+    same workspace serves a correct synchronous call afterwards."""
+    import torch
+    gold = load_golden("pool722.json")
+    eng = td.engine()
+    dem = torch.from_numpy(g.pool_demand()).cuda()
+    dist = torch.from_numpy(g.stand_distances(50)).cuda()
+    small = g.pool_demand(97, seed=13)
+    eng.pool_find_shards(torch.from_numpy(small).cuda(), torch.from_numpy(g.stand_distances(51)).cuda(), 3, 0, 3, 3)  # other shape first
+    out, cnt, token = eng.pool_find_shards(dem, dist, 4, 0, 8, 8, max_feasible=50_000, defer_stats=True)
+    st, overflowed = eng.pool_read_stats(token)
+    assert overflowed and (cnt.cpu().numpy() == -1).all()
+    assert [int(x.evaluated) for x in st] == g.POOL722_EVALUATED          # the counters stay exact
+    out, cnt, st = eng.pool_find_shards(dem, dist, 4, 0, 8, 8, max_feasible=50_000)
+    counts = cnt.cpu().numpy()
+    for s_ in range(8):
+        assert out[s_, : counts[s_]].cpu().numpy().tolist() == gold["shards"][s_]["plans"], s_
+
+
+def test_pool_5000_customers_reference_slices(td):
+    """north-star size: 5000 waiting customers.  Three slices (10 leading customers each) of the reference's own shard
+    rule with 512 shards were run through the compiled pool_n.c (tests/golden/make_golden.py --large-slices, ~10
+    CPU-minutes per slice); plans, feasible and kept counts must be identical, evaluated modulo 2^32 (pool_n.c:28).
+    Checked on the single-pass path and with a record list 3x too small (cost windows + alive pruning; a list that
+    cannot hold one cost level is grown by the host wrapper, so it must not be too small either)."""
+    import torch
+    gold = load_golden("pool5000_slices.json")
+    dem = g.pool_demand(gold["n"], seed=gold["seed"])
+    assert sha(dem) == gold["demand_sha256"]
+    eng = td.engine()
+    dd, ds = torch.from_numpy(dem).cuda(), torch.from_numpy(g.stand_distances(gold["n_stands"])).cuda()
+    for mf in (120_000_000, 20_000_000):
+        for sl in gold["slices"]:
+            out, cnt, st = eng.pool_find_shards(dd, ds, 4, sl["slice"], 1, gold["n_shards"], max_feasible=mf)
+            m = int(cnt[0])
+            assert out[0, :m].cpu().numpy().tolist() == sl["plans"], (mf, sl["slice"])
+            assert st[0].feasible == sl["stats"]["feasible"] and st[0].kept == sl["stats"]["kept"]
+            assert st[0].evaluated % (1 << 32) == sl["stats"]["evaluated_mod_2_32"]
+            assert (st[0].passes > 1) == (mf < sl["stats"]["feasible"])
 
 
 def test_pool_large_tables_take_the_global_memory_paths(td):
