@@ -86,6 +86,20 @@ int td_cost_matrix(const int32_t *dist, int n_stands,
                    int32_t fill, int32_t cutoff /* < 0: none */,
                    int32_t *cost_out /* n*n */, void *stream);
 
+/* Rows [row_begin, row_begin + row_count) of the same matrix, written to a row_count x n buffer: the multi-GPU path
+ * builds contiguous cab-row blocks per device (the loop of split.py:129-134 / Simulator.java:503-511 has no carried
+ * state, so rows split trivially).  workspace is optional (NULL: none): with td_cost_matrix_workspace_bytes() of
+ * scratch, big blocks take the grouped path -- rows of cabs standing at the same stand are identical, each distinct row
+ * is gathered once and streamed to all of them. */
+size_t td_cost_matrix_workspace_bytes(int n_stands, int row_count);
+int td_cost_matrix_rows(const int32_t *dist, int n_stands,
+                        const int32_t *cab_to, int n_cabs,
+                        const int32_t *cust_from, int n_cust,
+                        int32_t fill, int32_t cutoff /* < 0: none */,
+                        int row_begin, int row_count,
+                        int32_t *cost_out /* row_count*n */,
+                        void *workspace /* may be NULL */, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3  LCM greedy             replaces LCM(...) in heuristic.py:24-33, split.py:161-175,
  *     greedy_opt.py:61-82, simulate.py:76-97 and Simulator.LCM (Simulator.java:523-549).
@@ -146,6 +160,29 @@ int td_assign_exact_rect(const int32_t *cost, int n, int n_real_rows, int n_real
                          int32_t *col_of_row_out /* n */, int64_t *objective_out /* 1 */,
                          uint8_t *x_out /* n*n or NULL */, td_assign_stats *stats /* host, may be NULL */,
                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* Optimality certificate.  The solver ends with dual potentials u (per cab row) and v (per customer column) that
+ * prove its matching optimal by complementary slackness: cost[i][j] - u[i] - v[j] >= 0 on the real block and == 0 on
+ * the matched real cells; with spare (padding) rows or columns the potentials of the side that has spare members are
+ * <= 0 and == 0 where no real partner is matched.  sum u + sum v is then a lower bound of every assignment and equals
+ * the cost of this one.  td_assign_read_duals copies the potentials out of the workspace of the LAST solve (device
+ * int64[n] each); td_assign_certify evaluates the conditions with one sweep over the matrix and fills a DEVICE struct.
+ * This is what checks the exact optimum where an independent solver is too slow (scipy: minutes at n = 20 000).
+ * Certified semantics: solver.py:11-27 (min sum c x, every row and column sum = 1); invariant heuristic.py:40. */
+typedef struct td_assign_certificate {
+    int64_t min_reduced_cost;   /* min over the real block of cost - u - v          (must be >= 0) */
+    int64_t max_matched_slack;  /* max over matched real cells of |cost - u - v|    (must be == 0) */
+    int64_t dual_objective;     /* sum of u over real rows + sum of v over real columns */
+    int64_t matched_real_cost;  /* cost of the matched real cells                   (must equal dual_objective) */
+    int32_t sign_violations;    /* potentials with the wrong sign / nonzero on unused spare members (must be 0) */
+    int32_t reserved;
+} td_assign_certificate;
+int td_assign_read_duals(const void *workspace, int n, int n_real_rows, int n_real_cols,
+                         int64_t *u_out /* n */, int64_t *v_out /* n */, void *stream);
+size_t td_assign_certify_workspace_bytes(int n);
+int td_assign_certify(const int32_t *cost, int n, int n_real_rows, int n_real_cols, const int32_t *col_of_row,
+                      const int64_t *u, const int64_t *v, td_assign_certificate *cert_out /* device */,
+                      void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4  pool finder            replaces one `pool_n <pool-size> <thread> <file> <n> <out>` process

@@ -35,6 +35,11 @@ class AssignStats(ctypes.Structure):
                 ("unassigned_after_auction", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+class AssignCertificate(ctypes.Structure):
+    _fields_ = [("min_reduced_cost", ctypes.c_int64), ("max_matched_slack", ctypes.c_int64), ("dual_objective", ctypes.c_int64),
+                ("matched_real_cost", ctypes.c_int64), ("sign_violations", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 class PoolStats(ctypes.Structure):
     _fields_ = [("evaluated", ctypes.c_int64), ("feasible", ctypes.c_int64), ("kept", ctypes.c_int64),
                 ("rounds", ctypes.c_int32), ("passes", ctypes.c_int32)]
@@ -59,12 +64,18 @@ _SIGNATURES = {
     "td_prof_reset": (None, []),
     "td_prof_read": (_I, [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "td_cost_matrix": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp]),
+    "td_cost_matrix_workspace_bytes": (ctypes.c_size_t, [_I, _I]),
+    "td_cost_matrix_rows": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, _I, _I, c_vp, c_vp,
+                                ctypes.c_size_t, c_vp]),
     "td_lcm_workspace_bytes": (ctypes.c_size_t, [_I]),
     "td_lcm": (_I, [c_vp, _I, ctypes.POINTER(LcmParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "td_assign_workspace_bytes": (ctypes.c_size_t, [_I]),
     "td_assign_exact": (_I, [c_vp, _I, c_vp, c_vp, c_vp, ctypes.POINTER(AssignStats), c_vp, ctypes.c_size_t, c_vp]),
     "td_assign_rect_workspace_bytes": (ctypes.c_size_t, [_I, _I, _I]),
     "td_assign_exact_rect": (_I, [c_vp, _I, _I, _I, c_vp, c_vp, c_vp, ctypes.POINTER(AssignStats), c_vp, ctypes.c_size_t, c_vp]),
+    "td_assign_read_duals": (_I, [c_vp, _I, _I, _I, c_vp, c_vp, c_vp]),
+    "td_assign_certify_workspace_bytes": (ctypes.c_size_t, [_I]),
+    "td_assign_certify": (_I, [c_vp, _I, _I, _I, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "td_pool_workspace_bytes": (ctypes.c_size_t, [_I, _I, _I, ctypes.c_int64]),
     "td_pool_find": (_I, [c_vp, _I, c_vp, _I, _I, _I, _I, c_vp, ctypes.c_int32, c_vp, ctypes.POINTER(PoolStats),
                           c_vp, ctypes.c_size_t, ctypes.c_int64, c_vp]),

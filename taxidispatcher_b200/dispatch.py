@@ -26,7 +26,7 @@ import torch
 from . import _lib
 from ._lib import BIG_COST, INT32_MAX, POOL_REC_W, AssignStats, LcmParams, PoolStats, TaxiDispatchError, check
 
-__all__ = ["BIG_COST", "Engine", "calculate_cost", "solve", "solve_dispatch", "solve_full", "LCM", "LCM_heuristic",
+__all__ = ["BIG_COST", "Engine", "calculate_cost", "solve", "solve_dispatch", "solve_full", "solve_assignment", "LCM", "LCM_heuristic",
            "LCM_split", "LCM_greedy_opt", "LCM_simulate", "LCM_java", "find_pool", "find_pool_all", "find_pool_block",
            "find_pool_pairs", "pool_merge",
            "TaxiDispatchError"]
@@ -110,15 +110,21 @@ class Engine:
 
     # -- K1 ---------------------------------------------------------------------------------------
     def cost_matrix(self, dist: torch.Tensor, cab_to: torch.Tensor, cust_from: torch.Tensor, fill: int = BIG_COST,
-                    cutoff: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    cutoff: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                    rows: Optional[tuple] = None) -> torch.Tensor:
+        """Padded n x n matrix, or -- rows=(lo, hi) -- its cab-row block [lo, hi) as a (hi - lo) x n tensor."""
         n_cabs, n_cust = int(cab_to.numel()), int(cust_from.numel())
         n = max(n_cabs, n_cust)
         n_stands = int(dist.shape[0]) if dist.numel() else 0
+        lo, hi = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
         if out is None:
-            out = torch.empty((n, n), dtype=torch.int32, device=self.device)
-        rc = self.lib.td_cost_matrix(_ptr(dist), n_stands, _ptr(cab_to), n_cabs, _ptr(cust_from), n_cust, int(fill),
-                                     -1 if cutoff is None else int(cutoff), _ptr(out), _stream())
-        check(rc, "td_cost_matrix")
+            out = torch.empty((hi - lo, n), dtype=torch.int32, device=self.device)
+        nbytes = self.lib.td_cost_matrix_workspace_bytes(n_stands, hi - lo) if (hi - lo) * n >= (1 << 24) else 0
+        ws = self._workspace("cost", nbytes) if nbytes else None
+        rc = self.lib.td_cost_matrix_rows(_ptr(dist), n_stands, _ptr(cab_to), n_cabs, _ptr(cust_from), n_cust, int(fill),
+                                          -1 if cutoff is None else int(cutoff), lo, hi - lo, _ptr(out), _ptr(ws),
+                                          ws.numel() if ws is not None else 0, _stream())
+        check(rc, "td_cost_matrix_rows")
         return out
 
     # -- K3 ---------------------------------------------------------------------------------------
@@ -167,6 +173,33 @@ class Engine:
                                            ctypes.byref(st) if st is not None else None, _ptr(ws), ws.numel(), _stream())
         check(rc, "td_assign_exact_rect")
         return col[:n], obj, x, st
+
+    def assign_duals(self, n: int, n_real_rows: Optional[int] = None, n_real_cols: Optional[int] = None):
+        """Dual potentials (u per cab row, v per customer column; int64 device tensors) of the LAST assign() call."""
+        nr = n if n_real_rows is None else int(n_real_rows)
+        nc = n if n_real_cols is None else int(n_real_cols)
+        u = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        v = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        ws = self._ws["assign"]
+        check(self.lib.td_assign_read_duals(_ptr(ws), n, nr, nc, _ptr(u), _ptr(v), _stream()), "td_assign_read_duals")
+        return u[:n], v[:n]
+
+    def assign_certify(self, cost: torch.Tensor, col: torch.Tensor, u: torch.Tensor, v: torch.Tensor,
+                       n_real_rows: Optional[int] = None, n_real_cols: Optional[int] = None) -> dict:
+        """One sweep over the cost matrix: the complementary-slackness certificate of (col, u, v).  Returns the
+        td_assign_certificate fields plus `optimal` (all conditions hold)."""
+        n = int(cost.shape[0])
+        nr = n if n_real_rows is None else int(n_real_rows)
+        nc = n if n_real_cols is None else int(n_real_cols)
+        cert = torch.zeros(ctypes.sizeof(_lib.AssignCertificate), dtype=torch.uint8, device=self.device)
+        ws = self._workspace("certify", self.lib.td_assign_certify_workspace_bytes(n))
+        check(self.lib.td_assign_certify(_ptr(cost), n, nr, nc, _ptr(col), _ptr(u), _ptr(v), _ptr(cert), _ptr(ws), ws.numel(),
+                                         _stream()), "td_assign_certify")
+        c = _lib.AssignCertificate.from_buffer_copy(cert.cpu().numpy().tobytes())
+        out = {f: getattr(c, f) for f, _ in _lib.AssignCertificate._fields_ if f != "reserved"}
+        out["optimal"] = (c.min_reduced_cost >= 0 and c.max_matched_slack == 0 and c.sign_violations == 0 and
+                          c.dual_objective == c.matched_real_cost)
+        return out
 
     # -- K4 ---------------------------------------------------------------------------------------
     def pool_find(self, demand: torch.Tensor, dist: torch.Tensor, pool_size: int, shard: int = 0, n_shards: int = 8,
@@ -358,6 +391,25 @@ def solve_dispatch(distances, demand, cabs, fill: int = BIG_COST, cutoff: Option
     _, _, x, _ = engine().assign(cost_d, want_x=True, n_real_rows=max(len(cabs), 1) if len(cabs) < n else n,
                                  n_real_cols=max(len(demand), 1) if len(demand) < n else n)
     return n, x.cpu().numpy(), cost_d.cpu().numpy()
+
+
+def solve_assignment(dist_d: torch.Tensor, cab_to, cust_from, fill: int = BIG_COST, cutoff: Optional[int] = None):
+    """K1 + K2 for callers that only need the matching (split.py's range solves, the Simulator): stand indices in,
+    (n, col_of_row[n], cost_of_row[n]) out as small host arrays -- the n x n matrix and the n^2 solution vector never
+    leave the device.  dist_d is the stand table already on the device (it is shared by every range of a split).
+    cost_of_row[i] = cost[i][col_of_row[i]] (== fill for a dummy pairing, split.py:89)."""
+    n_cabs, n_cust = len(cab_to), len(cust_from)
+    n = max(n_cabs, n_cust)
+    if n == 0:
+        return 0, np.zeros(0, np.int32), np.zeros(0, np.int32)
+    eng = engine()
+    cab_d = _h2d_i32(cab_to) if n_cabs else torch.empty(0, dtype=torch.int32, device=eng.device)
+    cust_d = _h2d_i32(cust_from) if n_cust else torch.empty(0, dtype=torch.int32, device=eng.device)
+    cost_d = eng.cost_matrix(dist_d, cab_d, cust_d, fill, cutoff)
+    col, _, _, _ = eng.assign(cost_d, n_real_rows=max(n_cabs, 1) if n_cabs < n else n,
+                              n_real_cols=max(n_cust, 1) if n_cust < n else n)
+    picked = cost_d.gather(1, col.to(torch.int64).unsqueeze(1)).squeeze(1)      # n cells: plumbing, not compute
+    return n, _d2h(col), _d2h(picked)
 
 
 def LCM(n: int, c, mask_value: int = BIG_COST, stop_above: int = INT32_MAX, stop_at_value: int = INT32_MAX,

@@ -71,12 +71,75 @@ def _solve_range(solver, distances, split_demand, split_cabs):
     return s, rest_cust, rest_cabs
 
 
+def _solve_split_device(size: int, distances, demand, cabs, distributed: bool):
+    """solve_split on the engine without the host in the loop: the stand table is uploaded once, every range is a
+    boolean mask over the demand / cab arrays (split.py:31-38 `filter`), K1 and K2 run back to back on the device and
+    only the matching (n column indices + n picked costs per range) comes back -- the reference-shaped solver interface
+    would ship the n x n cost matrix and the n^2 solution vector to the host for every range."""
+    from . import dispatch
+    dem = np.asarray(demand, dtype=np.int64).reshape(-1, 3)
+    cab = np.asarray(cabs, dtype=np.int64).reshape(-1, 3)
+    dist_d = dispatch._h2d_i32(distances)
+    split_size = int(size / 4)
+    starts = list(range(0, size, split_size)) if split_size > 0 else []
+    rank, world = 0, 1
+    if distributed:
+        from . import parallel
+        rank, world = parallel.world()
+
+    def solve_block(d_rows, c_rows):
+        """(range total, unserved customer ids, unused cab ids) -- split.py:77-105"""
+        nb_cust, nb_cabs = len(d_rows), len(c_rows)
+        if nb_cust > 0 and nb_cabs > 0:
+            nb, col, picked = dispatch.solve_assignment(dist_d, c_rows[:, 2], d_rows[:, 1])
+            unserved = picked == BIG_COST                                        # split.py:89
+            s = int(picked[~unserved].astype(np.int64).sum())
+            if nb_cabs > nb_cust:                                                # there is always just one side dissatisfied
+                return s, np.zeros(0, np.int64), c_rows[np.nonzero(unserved)[0], 0]
+            return s, d_rows[col[unserved], 0], np.zeros(0, np.int64)
+        if nb_cust > 0:
+            return 0, d_rows[:, 0], np.zeros(0, np.int64)
+        return 0, np.zeros(0, np.int64), c_rows[:, 0]
+
+    results = {}
+    for idx, start in enumerate(starts):
+        if idx % world != rank:
+            continue
+        d_rows = dem[(dem[:, 1] >= start) & (dem[:, 1] < start + split_size)]
+        c_rows = cab[(cab[:, 2] >= start) & (cab[:, 2] < start + split_size)]
+        results[idx] = solve_block(d_rows, c_rows)
+    if distributed and world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world
+        dist.all_gather_object(gathered, results)            # a few hundred ids: latency, not bandwidth
+        results = {k: v for part in gathered for k, v in part.items()}
+    total = 0
+    rest_cust, rest_cabs = [], []
+    for idx in range(len(starts)):                            # range order, like the reference's while loop
+        s, rc, rb = results[idx]
+        total += s
+        rest_cust.append(np.asarray(rc, dtype=np.int64))
+        rest_cabs.append(np.asarray(rb, dtype=np.int64))
+    rest_cust = np.concatenate(rest_cust) if rest_cust else np.zeros(0, np.int64)
+    rest_cabs = np.concatenate(rest_cabs) if rest_cabs else np.zeros(0, np.int64)
+    rest_demand = dem[np.isin(dem[:, 0], rest_cust)]         # split.py:109-111: `filter` keeps the original order
+    rest_supply = cab[np.isin(cab[:, 0], rest_cabs)]
+    if len(rest_demand) == 0 and len(rest_supply) == 0:
+        return total
+    # the fifth run (split.py:113-119); count_sum adds every pairing below big_cost
+    nn, col, picked = dispatch.solve_assignment(dist_d, rest_supply[:, 2], rest_demand[:, 1])
+    return total + int(picked[picked < BIG_COST].astype(np.int64).sum())
+
+
 def solve_split(size: int, distances, demand, cabs, solver: Optional[Callable] = None, distributed: bool = False):
     """split.py:61-119.  Returns the total cost of the split solution, or None when there is no demand or no
-    supply (split.py:62-64).  distributed=True spreads the ranges over the ranks of the current process group."""
+    supply (split.py:62-64).  distributed=True spreads the ranges over the ranks of the current process group.
+    Without an injected `solver` the device path runs (_solve_split_device); a reference-shaped solver
+    (distances, demand, cabs) -> (n, x, cost) takes the literal restatement below (tests, oracle back ends)."""
     if len(demand) == 0 or len(cabs) == 0:
         return None
-    solver = solver or _default_solver()
+    if solver is None:
+        return _solve_split_device(size, distances, demand, cabs, distributed)
     split_size = int(size / 4)
     ranges = []
     start = 0

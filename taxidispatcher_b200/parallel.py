@@ -88,6 +88,41 @@ def gather_shard_plans(local: Sequence[Tuple[int, np.ndarray]], n: int, n_shards
     return [by_shard[s] for s in range(n_shards)]
 
 
+def cost_matrix_sharded(distances, cab_to, cust_from, fill: int = 250000, cutoff: Optional[int] = None,
+                        gather: bool = False, compute_rows: Optional[Callable] = None):
+    """calculate_cost (split.py:123-136) with the cab rows split across the ranks of the current process group: rank r
+    builds rows rows_for_rank(n, r, world) of the padded n x n matrix on its own device -- no exchange, the loop of
+    split.py:129-134 carries no state from row to row.  Returns (n, (lo, hi), block) with block a (hi - lo) x n int32
+    device tensor; gather=True all-gathers the blocks (one all_gather_into_tensor per call, padded to equal heights) and
+    returns the whole matrix on every rank instead.  compute_rows(lo, hi) -> array stands in for the device in CPU
+    tests."""
+    rank, w = world()
+    cab = np.ascontiguousarray(np.asarray(cab_to, dtype=np.int32))
+    cust = np.ascontiguousarray(np.asarray(cust_from, dtype=np.int32))
+    n = max(len(cab), len(cust))
+    lo, hi = rows_for_rank(n, rank, w)
+    if compute_rows is not None:
+        block = torch.as_tensor(np.asarray(compute_rows(lo, hi), dtype=np.int32).reshape(hi - lo, n))
+    else:
+        from . import dispatch
+        eng = dispatch.engine()
+        block = eng.cost_matrix(dispatch._h2d_i32(distances), dispatch._h2d_i32(cab), dispatch._h2d_i32(cust), fill, cutoff,
+                                rows=(lo, hi))
+    if not gather or w == 1:
+        return n, (lo, hi), block
+    height = (n + w - 1) // w                       # blocks differ by at most one row: pad to the common height
+    dev = _device_for_collectives()
+    mine = torch.zeros((height, n), dtype=torch.int32, device=dev)
+    mine[: hi - lo] = block.to(dev)
+    full = torch.empty((w * height, n), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(full, mine)
+    parts = []
+    for r in range(w):
+        rlo, rhi = rows_for_rank(n, r, w)
+        parts.append(full[r * height: r * height + (rhi - rlo)])
+    return n, (0, n), torch.cat(parts, dim=0)
+
+
 _SLOT_SHARD = {}
 
 

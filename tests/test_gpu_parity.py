@@ -61,6 +61,39 @@ def test_cost_matrix_full_size_properties(td):
     assert np.array_equal(got, np.abs(cab_to[rows][:, None] - cust_from[None, :]))
 
 
+def test_cost_matrix_row_blocks_and_grouped_path(td):
+    """Row blocks (the multi-GPU split of split.py:129-134) concatenate to the whole matrix, on the row-at-a-time kernel
+    and on the grouped kernel (rows bucketed by cab stand; taken for blocks >= 2^24 cells), with dummy rows, dummy
+    columns, the cutoff, an asymmetric table and n % 4 != 0 (grouped path declined)."""
+    import torch
+    from taxidispatcher_b200 import parallel as P
+    eng = td.engine()
+    rng = np.random.default_rng(404)
+    for n_cabs, n_cust, S, cutoff in ((5000, 4600, 300, None), (4096, 5000, 1000, 40), (4999, 4999, 64, None), (700, 650, 50, 10)):
+        dist = rng.integers(0, 90, (S, S)).astype(np.int32)
+        cab_to = rng.integers(0, S, n_cabs).astype(np.int32)
+        cust_from = rng.integers(0, S, n_cust).astype(np.int32)
+        n = max(n_cabs, n_cust)
+        ref = np.full((n, n), g.BIG_COST, np.int32)
+        blk = dist[cab_to][:, cust_from]
+        if cutoff is not None:
+            blk = np.where(blk < cutoff, blk, g.BIG_COST)
+        ref[:n_cabs, :n_cust] = blk
+        dd, dc, du = torch.from_numpy(dist).cuda(), torch.from_numpy(cab_to).cuda(), torch.from_numpy(cust_from).cuda()
+        whole = eng.cost_matrix(dd, dc, du, cutoff=cutoff).cpu().numpy()
+        assert np.array_equal(whole, ref), (n_cabs, n_cust, S)
+        for w in (2, 3):
+            parts = [eng.cost_matrix(dd, dc, du, cutoff=cutoff, rows=P.rows_for_rank(n, r, w)).cpu().numpy() for r in range(w)]
+            assert np.array_equal(np.concatenate(parts, axis=0), ref), (n_cabs, n_cust, S, w)
+    # the north-star shape through the public sharded entry point (one rank here: the whole matrix, grouped path)
+    cab_to, cust_from = g.config5b()
+    n, (lo, hi), block = P.cost_matrix_sharded(g.stand_distances(4000), cab_to, cust_from)
+    assert (n, lo, hi) == (20000, 0, 20000)
+    assert int(block.sum(dtype=torch.int64).item()) == int(np.abs(cab_to[:, None].astype(np.int64) - cust_from[None, :]).sum())
+    rows = [0, 5, 12345, 19999]
+    assert np.array_equal(block[rows].cpu().numpy(), np.abs(cab_to[rows][:, None] - cust_from[None, :]))
+
+
 # ---- K3 --------------------------------------------------------------------------------------------
 def _check_lcm(td, cost, **kw):
     n = cost.shape[0]
@@ -413,6 +446,76 @@ def test_assign_20k_north_star_objectives(td):
     col_h = col.cpu().numpy().astype(np.int64)
     assert sorted(col_h.tolist()) == list(range(20000))
     assert int(obj.item()) == 20000 == int(c5a.cpu().numpy()[np.arange(20000), col_h].sum())
+
+
+def _certify(td, cost, nr=None, nc=None):
+    """solve + dual certificate; returns (objective, certificate dict)"""
+    import torch
+    eng = td.engine()
+    c = torch.from_numpy(np.ascontiguousarray(cost, dtype=np.int32)).cuda() if isinstance(cost, np.ndarray) else cost
+    n = int(c.shape[0])
+    col, obj, _, _ = eng.assign(c, n_real_rows=nr, n_real_cols=nc)
+    u, v = eng.assign_duals(n, nr, nc)
+    cert = eng.assign_certify(c, col, u, v, nr, nc)
+    return int(obj.item()), col, u, v, cert
+
+
+def test_assign_dual_certificate(td):
+    """The potentials the solver ends with certify its matching (complementary slackness): feasible on the real block,
+    tight on the matched cells, dual objective == primal.  Checked against scipy where scipy is fast, and the checker
+    itself is shown to reject a perturbed matching / perturbed potentials."""
+    import torch
+    rng = np.random.default_rng(61)
+    for M in (g.config1a(), rng.integers(-50, 50, (301, 301)), rng.integers(0, 3, (260, 260)), g.config2_stand()[:1024, :1024]):
+        M = np.ascontiguousarray(M, dtype=np.int32)
+        obj, col, u, v, cert = _certify(td, M)
+        assert cert["optimal"], cert
+        assert obj == cert["dual_objective"] == assign_ref.solve_scipy(M)[0]
+    # unbalanced instances: padding rows (more customers than cabs) and padding columns (more cabs than customers)
+    for n_cabs, n_cust in ((218, 600), (600, 218), (351, 600), (64, 65)):
+        S = 50
+        dist = g.stand_distances(S)
+        cab_to = rng.integers(0, S, n_cabs)
+        cust_from = rng.integers(0, S, n_cust)
+        n, cost = cost_ref.calculate_cost_np(dist, cab_to.astype(np.int32), cust_from.astype(np.int32))
+        nr = n_cabs if n_cabs < n else None
+        nc = n_cust if n_cust < n else None
+        obj, col, u, v, cert = _certify(td, cost, nr, nc)
+        assert cert["optimal"], (n_cabs, n_cust, cert)
+        pad = g.BIG_COST * (n - min(n_cabs, n_cust))
+        assert obj == cert["matched_real_cost"] + pad == assign_ref.solve_scipy(cost)[0]
+    # the checker rejects what is not optimal
+    M = np.ascontiguousarray(g.config1a(), dtype=np.int32)
+    obj, col, u, v, cert = _certify(td, M)
+    eng = td.engine()
+    Md = torch.from_numpy(M).cuda()
+    col2 = col.clone()
+    col2[[0, 1]] = col[[1, 0]]                                       # another permutation: some matched cell is not tight
+    bad = eng.assign_certify(Md, col2, u, v)
+    assert not bad["optimal"] and (bad["max_matched_slack"] > 0 or bad["dual_objective"] != bad["matched_real_cost"])
+    u2 = u.clone()
+    u2[5] += 1                                                       # infeasible potentials
+    assert not eng.assign_certify(Md, col, u2, v)["optimal"]
+
+
+def test_assign_20k_certificates(td):
+    """north star: the exact optimum of 20 000 x 20 000 instances is PROVED by the dual certificate (one sweep) --
+    config 5-B (closed form known as well), config 5-A, and a random instance with no closed form at all."""
+    import torch
+    cab_to, cust_from = g.config5b()
+    a = torch.from_numpy(cab_to).cuda().to(torch.int32)
+    b = torch.from_numpy(cust_from).cuda().to(torch.int32)
+    cost = (a[:, None] - b[None, :]).abs().contiguous()
+    obj, col, u, v, cert = _certify(td, cost)
+    assert cert["optimal"] and obj == cert["dual_objective"] == 480177, cert
+    del cost
+    obj, col, u, v, cert = _certify(td, torch.from_numpy(g.config5a()).cuda())
+    assert cert["optimal"] and obj == cert["dual_objective"] == 20000, cert
+    gen = torch.Generator(device="cuda").manual_seed(20002)
+    cost = torch.randint(0, 100000, (20000, 20000), generator=gen, device="cuda", dtype=torch.int32)
+    obj, col, u, v, cert = _certify(td, cost)
+    assert cert["optimal"] and obj == cert["dual_objective"] == cert["matched_real_cost"], cert
+    assert sorted(col.cpu().numpy().tolist()) == list(range(20000))
 
 
 def test_assign_optimum_not_above_lcm(td):

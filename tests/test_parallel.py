@@ -50,6 +50,49 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _cost_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import cost_ref, gen_inputs as g
+    from taxidispatcher_b200 import parallel as P
+    d, cab_to, cust_from = g.config1b()          # 190 cabs x 200 customers: 10 dummy rows
+
+    def rows(lo, hi):                              # the literal loops of split.py:123-136 stand in for the device
+        return cost_ref.calculate_cost_np(d, cab_to, cust_from)[1][lo:hi]
+
+    n, (lo, hi), block = P.cost_matrix_sharded(d, cab_to, cust_from, compute_rows=rows)
+    n2, span, full = P.cost_matrix_sharded(d, cab_to, cust_from, gather=True, compute_rows=rows)
+    q.put((rank, n, lo, hi, block.numpy().tolist(), span, full.numpy().tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_cost_matrix_sharded_gloo(world):
+    """cab rows split over the ranks (north_star), blocks of unequal height, optional all-gather of the whole matrix"""
+    from oracle import cost_ref, gen_inputs as g
+    from taxidispatcher_b200 import parallel as P
+    d, cab_to, cust_from = g.config1b()
+    n_ref, ref = cost_ref.calculate_cost_np(d, cab_to, cust_from)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cost_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n, lo, hi, block, span, full in got:
+        assert n == n_ref and (lo, hi) == P.rows_for_rank(n, rank, world)
+        assert block == ref[lo:hi].tolist()
+        assert tuple(span) == (0, n) and full == ref.tolist()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_find_pool_sharded_gloo(world):
     from oracle import gen_inputs as g, pool_ref
