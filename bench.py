@@ -299,10 +299,12 @@ def main():
     my_shards = parallel.shards_for_rank(rank, world)     # contiguous block of logical shards
     slots = (8 + world - 1) // world
     cap = POOL_N // 2 + 1
+    # headed blocks (td_pool_find_shards_headed): a shard's survivors, their count and its counters travel together, so
+    # the multi-GPU step needs ONE collective; padding slots (ranks with fewer shards) keep their zero count for ever
+    blocks = torch.zeros((slots, cap + 1, 9), dtype=torch.int32, device=dev)
+    all_blocks = torch.zeros((world * slots, cap + 1, 9), dtype=torch.int32, device=dev)
     slot_plans = torch.zeros((slots, cap, 9), dtype=torch.int32, device=dev)
     slot_counts = torch.zeros(slots, dtype=torch.int32, device=dev)
-    all_plans = torch.zeros((world * slots, cap, 9), dtype=torch.int32, device=dev)
-    all_counts = torch.zeros(world * slots, dtype=torch.int32, device=dev)
     slot_shard_l = []
     for r in range(world):
         sh_r = parallel.shards_for_rank(r, world)
@@ -310,22 +312,24 @@ def main():
     slot_shard = torch.tensor(slot_shard_l, dtype=torch.int32, device=dev)
 
     def pool_step(want_stats=False):
-        stats = []
-        slot_counts.zero_()
-        if my_shards:                                        # ONE device call for all of this rank's shards
-            _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, my_shards[0], len(my_shards), 8,
-                                            out=slot_plans[: len(my_shards)], counts_out=slot_counts[: len(my_shards)],
-                                            want_stats=want_stats)
-            stats = st or []
-        if world > 1:
-            dist.all_gather_into_tensor(all_plans, slot_plans)
-            dist.all_gather_into_tensor(all_counts, slot_counts)
-            src_p, src_c = all_plans, all_counts
+        if want_stats:                                       # synchronous sizing / checking call (untimed)
+            stats = []
+            if my_shards:
+                _, _, stats = eng.pool_find_shards(dem_d, dist_d, POOL_K, my_shards[0], len(my_shards), 8,
+                                                   out=slot_plans[: len(my_shards)], counts_out=slot_counts[: len(my_shards)],
+                                                   want_stats=True)
         else:
-            src_p, src_c = slot_plans, slot_counts
+            stats = []
+        if my_shards:                                        # ONE asynchronous device call for all of this rank's shards
+            eng.pool_find_shards_headed(dem_d, dist_d, POOL_K, my_shards[0], len(my_shards), 8, out=blocks[: len(my_shards)])
+        if world > 1:
+            dist.all_gather_into_tensor(all_blocks, blocks)  # the only collective of the step
+            src = all_blocks
+        else:
+            src = blocks
         merged = cnt = None
         if rank == 0:
-            merged, cnt = eng.pool_merge_padded(src_p, src_c, slot_shard, POOL_N, POOL_K)
+            merged, cnt = eng.pool_merge_headed(src, slot_shard, POOL_N, POOL_K)
         return merged, cnt, stats
 
     # correctness gate (also the first warm-up): counts and merged result must equal the known answers
@@ -365,7 +369,7 @@ def main():
     launches = int(lib.td_launch_count())
     lib.td_prof_enable(0)
     # the timed steps ran asynchronously (no host round trip): make sure the last one was a complete, valid job
-    assert int(slot_counts[: len(my_shards)].min().item()) >= 0, "record list overflowed inside the timed region"
+    assert int(blocks[: max(len(my_shards), 1), 0, 0].min().item()) >= 0, "record list overflowed inside the timed region"
     if rank == 0:
         last = merged_last[0][: int(merged_last[1].item())].cpu().numpy()
         assert last.tolist() == golden, "timed steps produced a different result than the golden merge"

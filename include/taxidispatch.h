@@ -266,6 +266,20 @@ int td_pool_merge_padded(const int32_t *slot_plans, const int32_t *slot_counts, 
                          void *workspace, size_t workspace_bytes /* td_pool_merge_workspace_bytes(n_slots*cap, n) */,
                          void *stream);
 
+/* Headed blocks: the layout that travels through ONE collective in the multi-GPU path (findpool.c:149-160 collects
+ * out<i>.csv + out<i>.flg per shard; here a shard's survivors, their count and its counters are one block).
+ * blocks_out holds shard_count blocks of (cap + 1) rows of 9 int32: row 0 = header {count (-1: the record list
+ * overflowed), evaluated lo, evaluated hi, feasible lo, feasible hi, 0, 0, 0, 0}, rows 1.. = the plans.  Always
+ * asynchronous (no host out-parameters).  td_pool_merge_headed merges n_slots such blocks (slot_shard as above). */
+int td_pool_find_shards_headed(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
+                               int shard_begin, int shard_count, int n_shards,
+                               int32_t *blocks_out /* shard_count x (cap + 1) x 9 */, int32_t cap,
+                               void *workspace, size_t workspace_bytes, int64_t max_feasible, void *stream);
+int td_pool_merge_headed(const int32_t *blocks, const int32_t *slot_shard, int n_slots, int cap, int n, int pool_size,
+                         int32_t *plans_out /* n_slots*cap x 9 */, int32_t *n_plans_out /* 1 */,
+                         void *workspace, size_t workspace_bytes /* td_pool_merge_workspace_bytes(n_slots*cap, n) */,
+                         void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-buffer twins (allocate, copy, run, copy back).  Same semantics as above.
  * ------------------------------------------------------------------------------------------ */

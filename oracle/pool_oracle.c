@@ -5,7 +5,7 @@
  * called from tests/, from __graft_entry__.smoke() and from bench.py's cpu_baseline
  * leg, never from the product package.  Parity status: PINNED -- validated against the
  * compiled reference (oracle/_ref/pool_n_big, built from /root/reference/pool_n.c by
- * oracle/Makefile) on KAT P1/P2 of SURVEY.md section 4 (see tests/test_oracle_pool.py
+ * oracle/Makefile) on KAT P1/P2 of SURVEY.md section 4 (see tests/test_oracle.py
  * and tests/golden/pool_*.json).
  *
  * What it restates (reference file:line):

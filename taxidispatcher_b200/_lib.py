@@ -82,6 +82,9 @@ _SIGNATURES = {
     "td_pool_shards_workspace_bytes": (ctypes.c_size_t, [_I, _I, _I, _I, ctypes.c_int64]),
     "td_pool_find_shards": (_I, [c_vp, _I, c_vp, _I, _I, _I, _I, _I, c_vp, ctypes.c_int32, c_vp, ctypes.POINTER(PoolStats),
                                  c_vp, ctypes.c_size_t, ctypes.c_int64, c_vp]),
+    "td_pool_find_shards_headed": (_I, [c_vp, _I, c_vp, _I, _I, _I, _I, _I, c_vp, ctypes.c_int32, c_vp, ctypes.c_size_t,
+                                       ctypes.c_int64, c_vp]),
+    "td_pool_merge_headed": (_I, [c_vp, c_vp, _I, _I, _I, _I, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "td_pool_pairs_workspace_bytes": (ctypes.c_size_t, [_I]),
     "td_pool_pairs": (_I, [c_vp, c_vp, _I, c_vp, _I, _I, ctypes.c_double, c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "td_pool_read_stats": (_I, [c_vp, _I, ctypes.POINTER(PoolStats), ctypes.POINTER(ctypes.c_int), c_vp]),

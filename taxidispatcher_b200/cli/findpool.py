@@ -23,7 +23,7 @@ def main(argv=None) -> int:
     except OSError:
         print("Opening file %s failed" % fname)
         return 1
-    demand = formats.read_demand_csv(text, rec_number)
+    demand = formats.read_demand_csv(text, rec_number, pad_to=rec_number)   # ordersCount = rec-number whatever the file holds (pool_n.c:219-221)
     idx = np.arange(51, dtype=np.int32)
     dist = np.abs(idx[:, None] - idx[None, :]).astype(np.int32)
     plans, _ = dispatch.find_pool_all(demand, dist, pool_size, 8)

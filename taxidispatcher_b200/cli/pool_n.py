@@ -25,7 +25,7 @@ def main(argv=None) -> int:
     except OSError:
         print("Opening file %s failed" % fname)
         return 1
-    demand = formats.read_demand_csv(text, rec_number)
+    demand = formats.read_demand_csv(text, rec_number, pad_to=rec_number)   # ordersCount = rec-number whatever the file holds (pool_n.c:219-221)
     n_stands = 51                                                      # pool_n.c:15 MAX_STAND
     idx = np.arange(n_stands, dtype=np.int32)
     dist = np.abs(idx[:, None] - idx[None, :]).astype(np.int32)       # pool_n.c:179-185 setCosts

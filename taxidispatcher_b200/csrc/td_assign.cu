@@ -972,7 +972,12 @@ assign_kernel(AsgArgs a) {
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0 && part != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&ctrl->objective), (unsigned long long)part);
     grid.sync();
-    if (tid == 0) *a.objective_out = ctrl->objective;
+    // A solve that gave up (phase / level guards; cannot happen on finite integer costs) must not look like a result when
+    // the caller passed no stats: the matching is withdrawn (-1 everywhere) and the objective is INT64_MIN.
+    const bool failed = *reinterpret_cast<volatile int *>(&ctrl->status) != TD_OK;
+    if (failed)
+        for (int i = tid; i < n; i += nthreads) a.col_of_row_out[i] = -1;
+    if (tid == 0) *a.objective_out = failed ? LLONG_MIN : ctrl->objective;
 }
 
 static AsgArgs carve_assign(void *ws, int n, size_t *bytes) {

@@ -26,10 +26,13 @@
 // multi-GPU path builds contiguous cab-row blocks per rank (north_star: "cost-matrix rows are split
 // across devices").
 #include "td_common.cuh"
+#include <stdlib.h>
 
 namespace td {
 
 constexpr int kCostThreads = 256;
+__device__ int g_k1_store_mode = 0;   // EXPERIMENT
+__device__ __forceinline__ void st_out(int4 *p, int4 v, int mode) { if (mode == 0) __stcs(p, v); else if (mode == 1) *p = v; else __stwt(p, v); }
 
 __device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
     const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -50,6 +53,7 @@ cost_matrix_kernel(const int32_t *__restrict__ dist, int n_stands,
                    int row0, int row_end) {   // rows [row0, row_end) of the matrix; cost points at row row0
     extern __shared__ __align__(16) int32_t smem[];  // [2][row_stride] when kRowInSmem
     const int tid = threadIdx.x;
+    const int smode = g_k1_store_mode;
     const bool has_cut = cutoff >= 0;
     const bool vec_row = (n_stands & 3) == 0 && ((reinterpret_cast<uintptr_t>(dist) & 15) == 0);
     const bool vec_cust = (reinterpret_cast<uintptr_t>(cust_from) & 15) == 0;
@@ -89,7 +93,7 @@ cost_matrix_kernel(const int32_t *__restrict__ dist, int n_stands,
         int4 *outv = reinterpret_cast<int4 *>(out + h);
         if (!real_row) {
             const int4 f = make_int4(fill, fill, fill, fill);
-            for (int v = tid; v < nvec; v += kCostThreads) __stcs(outv + v, f);
+            for (int v = tid; v < nvec; v += kCostThreads) st_out(outv + v, f, smode);
         } else if (h == 0 && vec_cust) {
 #pragma unroll 2
             for (int v = tid; v < nvec; v += kCostThreads) {
@@ -101,7 +105,7 @@ cost_matrix_kernel(const int32_t *__restrict__ dist, int n_stands,
                 } else {
                     r.x = cell(j); r.y = cell(j + 1); r.z = cell(j + 2); r.w = cell(j + 3);
                 }
-                __stcs(outv + v, r);
+                st_out(outv + v, r, smode);
             }
         } else {
             for (int v = tid; v < nvec; v += kCostThreads) {
@@ -319,6 +323,8 @@ extern "C" int td_cost_matrix_rows(const int32_t *dist, int n_stands, const int3
     int per_sm = 8;
     if (smem > 0) { const int fit = int((200 * 1024) / smem); per_sm = fit < per_sm ? fit : per_sm; }
     per_sm = per_sm < 1 ? 1 : per_sm;
+    if (const char *e = getenv("TD_K1_PER_SM")) per_sm = atoi(e);   // EXPERIMENT
+    if (const char *e = getenv("TD_K1_STORE")) { int m = atoi(e); cudaMemcpyToSymbol(g_k1_store_mode, &m, sizeof m); }
     int grid = sms * per_sm;
     if (grid > row_count) grid = row_count;
     if (row_in_smem) {

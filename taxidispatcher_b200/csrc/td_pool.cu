@@ -984,11 +984,13 @@ pool_select_kernel(SelArgs a) {
 // kept plans -> ascending (cost, rank) -> pool_n.c:123-134 records
 __global__ void __launch_bounds__(1024)
 pool_emit_kernel(const PoolRec *__restrict__ kept_all, const PoolCtrl *ctrl, int K, int keep_cap, int32_t *plans_all,
-                 int32_t cap, int32_t *counts_out) {
+                 int32_t cap, int32_t *counts_out, int headed) {
+    // headed: every shard's block is (cap + 1) rows, row 0 is a header {count, evaluated lo, hi, feasible lo, hi, 0, 0, 0, 0}
+    // -- the block travels through ONE collective with its count and its counters (td_pool_find_shards_headed)
     const int slot = blockIdx.x;
     const PoolRec *kept = kept_all + size_t(slot) * keep_cap;
-    int32_t *plans_out = plans_all + size_t(slot) * cap * TD_POOL_REC_W;
-    int32_t *n_plans_out = counts_out + slot;
+    int32_t *block = plans_all + size_t(slot) * (cap + (headed ? 1 : 0)) * TD_POOL_REC_W;
+    int32_t *plans_out = block + (headed ? TD_POOL_REC_W : 0);
     const int m = int(ctrl->n_kept[slot]);
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         const PoolRec me = kept[i];
@@ -1022,48 +1024,160 @@ pool_emit_kernel(const PoolRec *__restrict__ kept_all, const PoolCtrl *ctrl, int
             row[8] = me.cost;
         }
     }
-    if (threadIdx.x == 0) *n_plans_out = (ctrl->overflow || ctrl->bad_input) ? -1 : m;  // -1: record list overflowed / unsupported input
+    if (threadIdx.x == 0) {
+        const int count = (ctrl->overflow || ctrl->bad_input) ? -1 : m;  // -1: record list overflowed / unsupported input
+        if (counts_out) counts_out[slot] = count;
+        if (headed) {
+            const unsigned long long ev = ctrl->evaluated[slot], fe = ctrl->feasible[slot];
+            block[0] = count;
+            block[1] = int32_t(unsigned(ev)); block[2] = int32_t(unsigned(ev >> 32));
+            block[3] = int32_t(unsigned(fe)); block[4] = int32_t(unsigned(fe >> 32));
+            block[5] = block[6] = block[7] = block[8] = 0;
+        }
+    }
 }
 
 // ---- merge (findpool.c:83-108) ---------------------------------------------------------------
-// One CTA.  Valid rows are compacted first (padded layout: row i belongs to slot i / cap and is
-// valid iff i % cap < counts[slot]; slot_shard[slot] = logical shard, concatenation order = shard
-// order).  Scan order = (column 8, concatenation position) for K == 4, concatenation position
-// otherwise (see header: findpool.c sorts on a column it never filled for K < 4).  Then the same
-// dominance rounds as pool_select on the small list.
+// One CTA.  Valid rows are compacted first (padded layout: slot s holds `cap` rows after `headed` header rows, row r of
+// the slot is valid iff r < count(s); slot_shard[slot] = logical shard, concatenation order = shard order).  Scan order =
+// (column 8, concatenation position) for K == 4, concatenation position otherwise (see header: findpool.c sorts on a
+// column it never filled for K < 4).  Then the same dominance rounds as pool_select on the small list.
+//
+// Up to kMergeFast valid rows (config 3: 678; 5000 customers: ~5000 of the 8 x 1250 possible) everything after the
+// compaction runs in shared memory: a bitonic sort of the 64-bit scan keys, dominance rounds with the SORTED POSITION as
+// a 32-bit key (native shared-memory atomicMin on a per-customer table), a block scan for the output positions.
+// More rows take the general path (ranks by counting, state in the global workspace).
+constexpr int kMergeFast = 8192;
 __global__ void __launch_bounds__(1024)
-pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, const int32_t *__restrict__ counts, int cap,
-                  const int32_t *__restrict__ slot_shard, unsigned long long *ckey /* total */, int32_t *crow /* total */,
-                  int32_t *order_key /* total */, int32_t *owner /* n */, uint8_t *state /* total */,
+pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, const int32_t *__restrict__ counts, int cap,
+                  int headed, const int32_t *__restrict__ slot_shard, unsigned long long *ckey /* total */,
+                  int32_t *crow /* total */, int32_t *order_key /* total */, int32_t *owner /* n */, uint8_t *state /* total */,
                   int32_t *plans_out, int32_t *n_plans_out) {
+    extern __shared__ __align__(16) unsigned char msm[];   // fast path: keys[kMergeFast] | rows[kMergeFast] | owner[n] | state[kMergeFast]
     __shared__ int s_m, s_live;
     __shared__ unsigned long long tile[1024];
+    __shared__ int s_scan[1024];
     const int tid = threadIdx.x;
+    const int slot_rows = cap + headed;
+    const int total = n_slots * cap;
+    auto row_ptr = [&](int ridx) { return plans + size_t(ridx) * TD_POOL_REC_W; };   // ridx: row index in the padded layout
     if (tid == 0) s_m = 0;
     __syncthreads();
     for (int base = 0; base < total; base += blockDim.x) {
         const int i = base + tid;
         bool ok = false;
         long long pos = 0;
+        int ridx = 0;
         if (i < total) {
-            if (counts) {
-                const int slot = i / cap, r = i % cap;
-                ok = r < counts[slot];
-                pos = (long long)(slot_shard ? slot_shard[slot] : slot) * cap + r;
-            } else {
-                ok = true; pos = i;
-            }
+            const int slot = i / cap, r = i % cap;
+            const int cnt = counts ? counts[slot] : (headed ? plans[size_t(slot) * slot_rows * TD_POOL_REC_W] : cap);
+            ok = r < cnt;
+            pos = (long long)(slot_shard ? slot_shard[slot] : slot) * cap + r;
+            ridx = slot * slot_rows + headed + r;
         }
         if (ok) {
             const int c = atomicAdd(&s_m, 1);
-            const unsigned long long costpart = K == TD_POOL_MAX_IN_POOL ? (unsigned long long)(unsigned)plans[size_t(i) * TD_POOL_REC_W + 8] : 0ull;
+            const unsigned long long costpart = K == TD_POOL_MAX_IN_POOL ? (unsigned long long)(unsigned)row_ptr(ridx)[8] : 0ull;
             ckey[c] = (costpart << 32) | (unsigned long long)pos;   // pos < 2^32 (total <= 2^24 rows)
-            crow[c] = i;
+            crow[c] = ridx;
         }
     }
     __syncthreads();
     const int m = s_m;
-    // rank = number of smaller keys (keys are unique)
+    if (m == 0) { if (tid == 0) *n_plans_out = 0; return; }
+
+    if (m <= kMergeFast && n <= TD_POOL_MAX_CUSTOMERS) {
+        unsigned long long *keys = reinterpret_cast<unsigned long long *>(msm);
+        int *rows = reinterpret_cast<int *>(msm + size_t(kMergeFast) * 8);
+        int *own = rows + kMergeFast;
+        uint8_t *st = reinterpret_cast<uint8_t *>(own + n);
+        int P = 1;
+        while (P < m) P <<= 1;
+        for (int i = tid; i < P; i += blockDim.x) {
+            keys[i] = i < m ? ckey[i] : ~0ull;
+            rows[i] = i < m ? crow[i] : -1;
+        }
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1)                       // bitonic sort, ascending; keys are unique
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < P; i += blockDim.x) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long a = keys[i], b2 = keys[l];
+                        const bool up = (i & k) == 0;
+                        if ((a > b2) == up) {
+                            keys[i] = b2; keys[l] = a;
+                            const int t = rows[i]; rows[i] = rows[l]; rows[l] = t;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = tid; i < m; i += blockDim.x) st[i] = 0;
+        for (;;) {   // dominance rounds: sorted position = scan rank
+            for (int c = tid; c < n; c += blockDim.x) own[c] = INT_MAX;
+            if (tid == 0) s_live = 0;
+            __syncthreads();
+            for (int i = tid; i < m; i += blockDim.x)
+                if (st[i] == 0) {
+                    s_live = 1;
+                    const int32_t *row = row_ptr(rows[i]);
+                    for (int q = 0; q < K; ++q) atomicMin(&own[row[q]], i);
+                }
+            __syncthreads();
+            if (!s_live) break;
+            for (int i = tid; i < m; i += blockDim.x)
+                if (st[i] == 0) {
+                    const int32_t *row = row_ptr(rows[i]);
+                    bool dom = true;
+                    for (int q = 0; q < K; ++q) dom = dom && own[row[q]] == i;
+                    if (dom) st[i] = 1;
+                }
+            __syncthreads();
+            for (int i = tid; i < m; i += blockDim.x)   // customers of kept plans are taken
+                if (st[i] == 1) {
+                    const int32_t *row = row_ptr(rows[i]);
+                    for (int q = 0; q < K; ++q) own[row[q]] = -1;
+                }
+            __syncthreads();
+            for (int i = tid; i < m; i += blockDim.x)
+                if (st[i] == 0) {
+                    const int32_t *row = row_ptr(rows[i]);
+                    bool hit = false;
+                    for (int q = 0; q < K; ++q) hit = hit || own[row[q]] == -1;
+                    if (hit) st[i] = 2;
+                }
+            __syncthreads();
+        }
+        // output position of a kept row = number of kept rows before it in the sorted order (block scan over chunks)
+        const int per = (m + blockDim.x - 1) / blockDim.x;
+        const int lo = min(tid * per, m), hi = min(lo + per, m);
+        int cnt = 0;
+        for (int i = lo; i < hi; ++i) cnt += st[i] == 1;
+        s_scan[tid] = cnt;
+        __syncthreads();
+        if (tid < 32) {   // exclusive scan of the 1024 chunk counts: 32 per lane, warp scan of the lane sums
+            int run = 0;
+            for (int k2 = 0; k2 < 32; ++k2) run += s_scan[tid * 32 + k2];
+            int incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+            int acc = incl - run;
+            for (int k2 = 0; k2 < 32; ++k2) { const int v = s_scan[tid * 32 + k2]; s_scan[tid * 32 + k2] = acc; acc += v; }
+            if (tid == 31) *n_plans_out = incl;
+        }
+        __syncthreads();
+        int pos = s_scan[tid];
+        for (int i = lo; i < hi; ++i)
+            if (st[i] == 1) {
+                const int32_t *row = row_ptr(rows[i]);
+                for (int t = 0; t < TD_POOL_REC_W; ++t) plans_out[size_t(pos) * TD_POOL_REC_W + t] = row[t];
+                ++pos;
+            }
+        return;
+    }
+
+    // ---- general path: rank = number of smaller keys (keys are unique) -----------------------------------------------
     for (int base = 0; base < m; base += blockDim.x) {
         const int me = base + tid;
         const unsigned long long mine = me < m ? ckey[me] : ~0ull;
@@ -1085,14 +1199,14 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, co
         for (int i = tid; i < m; i += blockDim.x)
             if (state[i] == 0) {
                 s_live = 1;
-                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+                const int32_t *row = row_ptr(crow[i]);
                 for (int q = 0; q < K; ++q) atomicMin(&owner[row[q]], order_key[i]);
             }
         __syncthreads();
         if (!s_live) break;
         for (int i = tid; i < m; i += blockDim.x)
             if (state[i] == 0) {
-                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+                const int32_t *row = row_ptr(crow[i]);
                 bool dom = true;
                 for (int q = 0; q < K; ++q) dom = dom && owner[row[q]] == order_key[i];
                 if (dom) state[i] = 1;
@@ -1101,13 +1215,13 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, co
         // customers of kept plans are taken: every other live plan touching them dies
         for (int i = tid; i < m; i += blockDim.x)
             if (state[i] == 1) {
-                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+                const int32_t *row = row_ptr(crow[i]);
                 for (int q = 0; q < K; ++q) owner[row[q]] = -1;
             }
         __syncthreads();
         for (int i = tid; i < m; i += blockDim.x)
             if (state[i] == 0) {
-                const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+                const int32_t *row = row_ptr(crow[i]);
                 bool hit = false;
                 for (int q = 0; q < K; ++q) hit = hit || owner[row[q]] == -1;
                 if (hit) state[i] = 2;
@@ -1121,7 +1235,7 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int total, int n, int K, co
         if (state[i] == 1) {
             int pos = 0;
             for (int j = 0; j < m; ++j) pos += (state[j] == 1 && order_key[j] < order_key[i]);
-            const int32_t *row = plans + size_t(crow[i]) * TD_POOL_REC_W;
+            const int32_t *row = row_ptr(crow[i]);
             for (int t = 0; t < TD_POOL_REC_W; ++t) plans_out[size_t(pos) * TD_POOL_REC_W + t] = row[t];
             atomicAdd(&s_m, 1);
         }
@@ -1276,14 +1390,36 @@ extern "C" size_t td_pool_workspace_bytes(int n, int n_stands, int pool_size, in
     return td_pool_shards_workspace_bytes(n, n_stands, pool_size, 1, max_feasible);
 }
 
+static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
+                                 int shard_begin, int shard_count, int n_shards, int32_t *plans_out, int32_t cap,
+                                 int32_t *counts_out, td_pool_stats *stats, void *workspace, size_t workspace_bytes,
+                                 int64_t max_feasible, void *stream, int headed);
+
 extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
                                    int shard_begin, int shard_count, int n_shards, int32_t *plans_out, int32_t cap,
                                    int32_t *counts_out, td_pool_stats *stats, void *workspace, size_t workspace_bytes,
                                    int64_t max_feasible, void *stream) {
+    if (!counts_out) return TD_ERR_INVALID;
+    return pool_find_shards_impl(demand, n, dist, n_stands, pool_size, shard_begin, shard_count, n_shards, plans_out, cap, counts_out,
+                                 stats, workspace, workspace_bytes, max_feasible, stream, 0);
+}
+
+extern "C" int td_pool_find_shards_headed(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
+                                          int shard_begin, int shard_count, int n_shards, int32_t *blocks_out, int32_t cap,
+                                          void *workspace, size_t workspace_bytes, int64_t max_feasible, void *stream) {
+    if (!blocks_out) return TD_ERR_INVALID;
+    return pool_find_shards_impl(demand, n, dist, n_stands, pool_size, shard_begin, shard_count, n_shards, blocks_out, cap, nullptr,
+                                 nullptr, workspace, workspace_bytes, max_feasible, stream, 1);
+}
+
+static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *dist, int n_stands, int pool_size,
+                                 int shard_begin, int shard_count, int n_shards, int32_t *plans_out, int32_t cap,
+                                 int32_t *counts_out, td_pool_stats *stats, void *workspace, size_t workspace_bytes,
+                                 int64_t max_feasible, void *stream, int headed) {
     using namespace td;
     if (pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || n < 0 || n > TD_POOL_MAX_CUSTOMERS || n_stands <= 0 ||
         n_shards < 1 || shard_begin < 0 || shard_count < 1 || shard_count > kMaxSlots || shard_begin + shard_count > n_shards ||
-        cap < 0 || !counts_out || max_feasible < 0)
+        cap < 0 || (!counts_out && !headed) || max_feasible < 0)
         return TD_ERR_INVALID;
     if (n_stands > 32767) return TD_ERR_INVALID;
     if (!have_device()) return TD_ERR_NO_DEVICE;
@@ -1294,7 +1430,9 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
     const long long stop64 = (long long)step * (shard_begin + shard_count);
     const int stop = stop64 > n ? n : int(stop64);                            // pool_n.c:228
     if (n == 0 || start >= n) {
-        TD_CUDA_TRY(cudaMemsetAsync(counts_out, 0, sizeof(int32_t) * shard_count, st));
+        if (counts_out) TD_CUDA_TRY(cudaMemsetAsync(counts_out, 0, sizeof(int32_t) * shard_count, st));
+        if (headed && plans_out)   // empty blocks: header count 0
+            TD_CUDA_TRY(cudaMemsetAsync(plans_out, 0, sizeof(int32_t) * size_t(shard_count) * (cap + 1) * TD_POOL_REC_W, st));
         if (stats) TD_CUDA_TRY(cudaStreamSynchronize(st));
         return TD_OK;
     }
@@ -1377,7 +1515,7 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
         if (rc != TD_OK) return rc;
         rc = run_select(true, INT_MAX);
         if (rc != TD_OK) return rc;
-        pool_emit_kernel<<<shard_count, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, keep_cap, plans_out, cap, counts_out);
+        pool_emit_kernel<<<shard_count, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, keep_cap, plans_out, cap, counts_out, headed);
         TD_LAUNCH_CHECK();
         return TD_OK;
     }
@@ -1452,7 +1590,7 @@ extern "C" int td_pool_find_shards(const int32_t *demand, int n, const int32_t *
         if (cost_hi == INT_MAX) break;
         cost_lo = cost_hi;
     }
-    pool_emit_kernel<<<shard_count, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, keep_cap, plans_out, cap, counts_out);
+    pool_emit_kernel<<<shard_count, 1024, 0, st>>>(w.kept, w.ctrl, pool_size, keep_cap, plans_out, cap, counts_out, headed);
     TD_LAUNCH_CHECK();
     TD_CUDA_TRY(cudaMemcpyAsync(&h, w.ctrl, offsetof(PoolCtrl, pass_begin_marker), cudaMemcpyDeviceToHost, st));
     TD_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1559,6 +1697,20 @@ static MergeWs carve_merge(void *ws, int total, int n) {
 
 extern "C" size_t td_pool_merge_workspace_bytes(int total_plans, int n) { return td::carve_merge(nullptr, total_plans, n).bytes; }
 
+namespace td {
+static int launch_merge(const int32_t *plans, int n_slots, int cap, int headed, const int32_t *counts, const int32_t *slot_shard,
+                        int n, int pool_size, int32_t *plans_out, int32_t *n_plans_out, void *workspace, cudaStream_t st) {
+    const int total = n_slots * cap;
+    MergeWs w = carve_merge(workspace, total, n);
+    const size_t smem = n <= TD_POOL_MAX_CUSTOMERS ? size_t(kMergeFast) * 13 + size_t(n) * 4 + 16 : 0;   // keys + rows + state + owner
+    if (smem) TD_CUDA_TRY(cudaFuncSetAttribute(pool_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    pool_merge_kernel<<<1, 1024, smem, st>>>(plans, n_slots, n, pool_size, counts, cap, headed, slot_shard, w.ckey, w.crow,
+                                             w.order_key, w.owner, w.state, plans_out, n_plans_out);
+    TD_LAUNCH_CHECK();
+    return TD_OK;
+}
+}  // namespace td
+
 extern "C" int td_pool_merge(const int32_t *shard_plans, int total_plans, int n, int pool_size, int32_t *plans_out,
                              int32_t *n_plans_out, void *workspace, size_t workspace_bytes, void *stream) {
     using namespace td;
@@ -1568,11 +1720,7 @@ extern "C" int td_pool_merge(const int32_t *shard_plans, int total_plans, int n,
     if (total_plans == 0) { TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st)); return TD_OK; }
     if (!shard_plans || !plans_out || !workspace) return TD_ERR_INVALID;
     if (workspace_bytes < td_pool_merge_workspace_bytes(total_plans, n)) return TD_ERR_WORKSPACE;
-    MergeWs w = carve_merge(workspace, total_plans, n);
-    pool_merge_kernel<<<1, 1024, 0, st>>>(shard_plans, total_plans, n, pool_size, nullptr, 1, nullptr, w.ckey, w.crow, w.order_key,
-                                          w.owner, w.state, plans_out, n_plans_out);
-    TD_LAUNCH_CHECK();
-    return TD_OK;
+    return launch_merge(shard_plans, 1, total_plans, 0, nullptr, nullptr, n, pool_size, plans_out, n_plans_out, workspace, st);   // one slot, every row valid
 }
 
 extern "C" int td_pool_merge_padded(const int32_t *slot_plans, const int32_t *slot_counts, const int32_t *slot_shard,
@@ -1588,9 +1736,21 @@ extern "C" int td_pool_merge_padded(const int32_t *slot_plans, const int32_t *sl
     if (total == 0) { TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st)); return TD_OK; }
     if (!slot_plans || !slot_counts || !plans_out || !workspace) return TD_ERR_INVALID;
     if (workspace_bytes < td_pool_merge_workspace_bytes(total, n)) return TD_ERR_WORKSPACE;
-    MergeWs w = carve_merge(workspace, total, n);
-    pool_merge_kernel<<<1, 1024, 0, st>>>(slot_plans, total, n, pool_size, slot_counts, cap, slot_shard, w.ckey, w.crow,
-                                          w.order_key, w.owner, w.state, plans_out, n_plans_out);
-    TD_LAUNCH_CHECK();
-    return TD_OK;
+    return launch_merge(slot_plans, n_slots, cap, 0, slot_counts, slot_shard, n, pool_size, plans_out, n_plans_out, workspace, st);
+}
+
+extern "C" int td_pool_merge_headed(const int32_t *blocks, const int32_t *slot_shard, int n_slots, int cap, int n, int pool_size,
+                                    int32_t *plans_out, int32_t *n_plans_out, void *workspace, size_t workspace_bytes,
+                                    void *stream) {
+    using namespace td;
+    if (n_slots < 0 || cap < 1 || n < 0 || pool_size < 2 || pool_size > TD_POOL_MAX_IN_POOL || !n_plans_out) return TD_ERR_INVALID;
+    if (!have_device()) return TD_ERR_NO_DEVICE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total64 = (long long)n_slots * cap;
+    if (total64 > (1 << 24)) return TD_ERR_INVALID;
+    const int total = int(total64);
+    if (total == 0) { TD_CUDA_TRY(cudaMemsetAsync(n_plans_out, 0, sizeof(int32_t), st)); return TD_OK; }
+    if (!blocks || !plans_out || !workspace) return TD_ERR_INVALID;
+    if (workspace_bytes < td_pool_merge_workspace_bytes(total, n)) return TD_ERR_WORKSPACE;
+    return launch_merge(blocks, n_slots, cap, 1, nullptr, slot_shard, n, pool_size, plans_out, n_plans_out, workspace, st);
 }

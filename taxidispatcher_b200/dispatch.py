@@ -271,6 +271,60 @@ class Engine:
             return out, cnt, (list(st) if want_stats else None)
         raise TaxiDispatchError(_lib.TD_ERR_CAPACITY, "td_pool_find_shards")
 
+    def pool_find_shards_headed(self, demand: torch.Tensor, dist: torch.Tensor, pool_size: int, shard_begin: int,
+                                shard_count: int, n_shards: int, out: torch.Tensor, max_feasible: Optional[int] = None):
+        """Asynchronous single pass into headed blocks: out is [shard_count, cap + 1, 9] int32 (device), row 0 of every
+        block = {count, evaluated lo / hi, feasible lo / hi, ...} (td_pool_find_shards_headed).  Needs a record capacity
+        that holds every feasible plan -- remembered by an earlier synchronous pool_find_shards call of the same shape."""
+        n = int(demand.shape[0])
+        n_stands = int(dist.shape[0])
+        cap = int(out.shape[1]) - 1
+        key = ("pool_mf", n, pool_size, shard_count)
+        mf = int(max_feasible) if max_feasible is not None else self._ws.get(key, (1 << 21) * min(shard_count, 4))
+        nbytes = self.lib.td_pool_shards_workspace_bytes(n, n_stands, pool_size, shard_count, mf)
+        ws = self._workspace("pool", nbytes)
+        rc = self.lib.td_pool_find_shards_headed(_ptr(demand), n, _ptr(dist), n_stands, pool_size, shard_begin, shard_count,
+                                                 n_shards, _ptr(out), cap, _ptr(ws), ws.numel(), mf, _stream())
+        check(rc, "td_pool_find_shards_headed")
+        return out
+
+    def pool_merge_headed(self, blocks: torch.Tensor, slot_shard: Optional[torch.Tensor], n: int, pool_size: int):
+        """blocks [n_slots, cap + 1, 9] headed blocks (device).  Returns (plans, count) device tensors."""
+        n_slots, cap = int(blocks.shape[0]), int(blocks.shape[1]) - 1
+        total = n_slots * cap
+        out = torch.empty((max(total, 1), POOL_REC_W), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ws = self._workspace("merge", self.lib.td_pool_merge_workspace_bytes(total, n))
+        rc = self.lib.td_pool_merge_headed(_ptr(blocks), _ptr(slot_shard), n_slots, cap, n, pool_size, _ptr(out), _ptr(cnt),
+                                           _ptr(ws), ws.numel(), _stream())
+        check(rc, "td_pool_merge_headed")
+        return out, cnt
+
+    def pool_merge_headed_packed(self, blocks: torch.Tensor, slot_shard: Optional[torch.Tensor], n: int, pool_size: int):
+        """Merge of headed blocks with everything the host wants in ONE buffer: row 0 = {merged count}, rows 1..n//pool_size
+        = the merged plans, then one header row per block.  One device->host copy completes a whole `findpool` job."""
+        n_slots, cap = int(blocks.shape[0]), int(blocks.shape[1]) - 1
+        total = n_slots * cap
+        keep = n // pool_size + 1                                     # merged plans are customer-disjoint
+        pack = torch.empty((1 + max(total, keep) + n_slots, POOL_REC_W), dtype=torch.int32, device=self.device)
+        ws = self._workspace("merge", self.lib.td_pool_merge_workspace_bytes(total, n))
+        rc = self.lib.td_pool_merge_headed(_ptr(blocks), _ptr(slot_shard), n_slots, cap, n, pool_size,
+                                           ctypes.c_void_p(pack.data_ptr() + 4 * POOL_REC_W), _ptr(pack), _ptr(ws), ws.numel(),
+                                           _stream())
+        check(rc, "td_pool_merge_headed")
+        pack[1 + keep: 1 + keep + n_slots] = blocks[:, 0, :]          # the headers ride along (a few hundred bytes)
+        host = _d2h(pack[: 1 + keep + n_slots])
+        m = int(host[0, 0])
+        counts, ev, fe = self.headers_host_view(host[1 + keep:])
+        return host[1: 1 + m].copy(), counts, ev, fe
+
+    @staticmethod
+    def headers_host_view(headers: np.ndarray):
+        """headers: [n_slots, 9] int32 header rows -> (counts, evaluated, feasible) int64 arrays"""
+        h = np.asarray(headers).astype(np.int64) & 0xFFFFFFFF
+        counts = np.asarray(headers)[:, 0].astype(np.int64)
+        return counts, h[:, 1] | (h[:, 2] << 32), h[:, 3] | (h[:, 4] << 32)
+
     def pool_read_stats(self, token):
         """Completes a defer_stats=True call: waits for the stream, returns (stats list, overflowed)."""
         ws, shard_count = token
@@ -388,8 +442,10 @@ def solve_dispatch(distances, demand, cabs, fill: int = BIG_COST, cutoff: Option
     if n == 0:
         return 0, [], 0
     # every real call is unbalanced (dummy rows / columns of `fill`): only the real block is searched
-    _, _, x, _ = engine().assign(cost_d, want_x=True, n_real_rows=max(len(cabs), 1) if len(cabs) < n else n,
-                                 n_real_cols=max(len(demand), 1) if len(demand) < n else n)
+    _, obj, x, _ = engine().assign(cost_d, want_x=True, n_real_rows=max(len(cabs), 1) if len(cabs) < n else n,
+                                   n_real_cols=max(len(demand), 1) if len(demand) < n else n)
+    if int(obj.item()) == -(1 << 63):              # the kernel withdraws its result when it gave up (td_assign.cu)
+        raise TaxiDispatchError(_lib.TD_ERR_NOT_CONVERGED, "td_assign_exact_rect")
     return n, x.cpu().numpy(), cost_d.cpu().numpy()
 
 
@@ -408,8 +464,11 @@ def solve_assignment(dist_d: torch.Tensor, cab_to, cust_from, fill: int = BIG_CO
     cost_d = eng.cost_matrix(dist_d, cab_d, cust_d, fill, cutoff)
     col, _, _, _ = eng.assign(cost_d, n_real_rows=max(n_cabs, 1) if n_cabs < n else n,
                               n_real_cols=max(n_cust, 1) if n_cust < n else n)
+    col_h = _d2h(col)
+    if n and int(col_h.min()) < 0:                 # the kernel withdraws the matching when it gave up (td_assign.cu)
+        raise TaxiDispatchError(_lib.TD_ERR_NOT_CONVERGED, "td_assign_exact_rect")
     picked = cost_d.gather(1, col.to(torch.int64).unsqueeze(1)).squeeze(1)      # n cells: plumbing, not compute
-    return n, _d2h(col), _d2h(picked)
+    return n, col_h, _d2h(picked)
 
 
 def LCM(n: int, c, mask_value: int = BIG_COST, stop_above: int = INT32_MAX, stop_at_value: int = INT32_MAX,
@@ -516,15 +575,19 @@ def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
     stats = {"evaluated": 0, "feasible": 0, "kept_per_shard": [], "rounds": 0}
     fast_key = ("pool_single_pass_ok", n, pool_size, n_shards)
     if n_shards <= 64 and eng._ws.get(fast_key):
-        # steady state: enumeration, selection and merge are queued back to back, ONE host synchronisation
-        out, cnt, token = eng.pool_find_shards(dem, d, pool_size, 0, n_shards, n_shards, defer_stats=True)
-        merged, mcnt = eng.pool_merge_padded(out, cnt, None, n, pool_size)
-        st, overflowed = eng.pool_read_stats(token)
-        if not overflowed:
-            m = _d2h_int(mcnt)
-            stats.update(evaluated=sum(int(s.evaluated) for s in st), feasible=sum(int(s.feasible) for s in st),
-                         rounds=int(st[0].rounds), kept_per_shard=[int(s.kept) for s in st], kept=m)
-            return _d2h(merged[:m]), stats
+        # steady state: enumeration, selection and merge are queued back to back into headed blocks; ONE device->host copy
+        # (merged plans + count + the per-shard counters) and one synchronisation complete the job
+        cap = n // 2 + 1
+        bkey = ("pool_blocks", n, n_shards)
+        blocks = eng._ws.get(bkey)
+        if blocks is None:
+            blocks = eng._ws[bkey] = torch.zeros((n_shards, cap + 1, POOL_REC_W), dtype=torch.int32, device=eng.device)
+        eng.pool_find_shards_headed(dem, d, pool_size, 0, n_shards, n_shards, out=blocks)
+        plans, counts, ev, fe = eng.pool_merge_headed_packed(blocks, None, n, pool_size)
+        if int(counts.min()) >= 0:
+            stats.update(evaluated=int(ev.sum()), feasible=int(fe.sum()), kept_per_shard=[int(c) for c in counts],
+                         kept=len(plans))
+            return plans, stats
         eng._ws[fast_key] = False                         # input outgrew the record list: cost windows below
     parts, counts = [], []
     single = True

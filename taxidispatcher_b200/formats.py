@@ -16,19 +16,36 @@ import numpy as np
 REC_W = 9
 
 
-def read_demand_csv(text: str, max_rows: int | None = None) -> np.ndarray:
-    """pool_n.c:42-52: up to five comma separated ints per line, row order = customer index."""
+def _atoi(tok: str) -> int:
+    """C atoi: optional blanks, optional sign, leading digits; anything else is 0."""
+    t = tok.lstrip(" \t\n\v\f\r")
+    i = 1 if t[:1] in "+-" else 0
+    j = i
+    while j < len(t) and t[j].isdigit():
+        j += 1
+    return int(t[:j]) if j > i else 0
+
+
+def read_demand_csv(text: str, max_rows: int | None = None, pad_to: int | None = None) -> np.ndarray:
+    """readDemand (pool_n.c:30-54), literally: fgets with a 40-byte buffer (a longer line continues in the next record),
+    strtok on ',', atoi on up to five fields; fields that are not given keep the zero of the static array, and so does
+    every record the file does not reach.  A blank line is a record (of zeros), exactly as in the reference.
+    max_rows = the reference's `linesNumb` (stop after that many records); pad_to: number of rows of the result
+    (the reference always searches `rec-number` records, pool_n.c:221,229 -- rows past the end of the file are zeros)."""
     rows = []
-    for line in text.splitlines():
-        if max_rows is not None and len(rows) >= max_rows:
-            break
-        f = [v for v in line.strip().split(",") if v != ""]
-        if not f:
-            continue
+    pos, n_text = 0, len(text)
+    while pos < n_text and (max_rows is None or len(rows) < max_rows):
+        end = text.find("\n", pos, pos + 39)              # fgets: at most 39 characters, stops after a newline
+        nxt = end + 1 if end >= 0 else min(pos + 39, n_text)
+        line = text[pos:nxt]
+        pos = nxt
+        toks = [t for t in line.split(",") if t != ""]    # strtok skips empty fields
         r = [0, 0, 0, 0, 0]
-        for i, v in enumerate(f[:5]):
-            r[i] = int(v)          # atoi
+        for i, tok in enumerate(toks[:5]):
+            r[i] = _atoi(tok)
         rows.append(r)
+    if pad_to is not None:
+        rows = rows[:pad_to] + [[0, 0, 0, 0, 0]] * max(0, pad_to - len(rows))
     return np.asarray(rows, dtype=np.int32).reshape(-1, 5)
 
 

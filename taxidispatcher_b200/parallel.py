@@ -127,10 +127,11 @@ _SLOT_SHARD = {}
 
 
 def _find_pool_sharded_device(dem: np.ndarray, dist_table, pool_size: int, n_shards: int, rank: int, w: int, mine: List[int]):
-    """Device-resident product path (NCCL): this rank's block of shards in one asynchronous device call, the
-    survivors gathered into every rank's merge input without touching the host, merge on the device, ONE read-back.
-    Returns None (on every rank together) when some rank's record list overflowed -- the caller then takes the
-    synchronous path, which sizes the list for the next call."""
+    """Device-resident product path (NCCL): this rank's block of shards in one asynchronous device call into HEADED blocks
+    (survivors + their count + the shard's counters, td_pool_find_shards_headed), ONE all_gather into every rank's merge
+    input, merge on the device, ONE read-back.  No stats all_reduce, no second collective, no host round trip before the
+    merge.  Returns None (on every rank together: all ranks see the same headers) when some rank's record list
+    overflowed -- the caller then takes the synchronous path, which sizes the list for the next call."""
     from . import dispatch
     eng = dispatch.engine()
     dev = eng.device
@@ -139,43 +140,27 @@ def _find_pool_sharded_device(dem: np.ndarray, dist_table, pool_size: int, n_sha
     slots = (n_shards + w - 1) // w
     dem_d = dispatch._h2d_i32(dem)
     dist_d = dispatch._h2d_i32(dist_table)
-    slot_plans = torch.zeros((slots, cap, REC_W), dtype=torch.int32, device=dev)
-    slot_counts = torch.zeros(slots, dtype=torch.int32, device=dev)
-    token = None
-    if mine:
-        _, _, token = eng.pool_find_shards(dem_d, dist_d, pool_size, mine[0], len(mine), n_shards,
-                                           out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)], defer_stats=True)
-    all_plans = torch.empty((w * slots, cap, REC_W), dtype=torch.int32, device=dev)
-    all_counts = torch.empty(w * slots, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(all_plans, slot_plans)
-    dist.all_gather_into_tensor(all_counts, slot_counts)
-    key = (w, n_shards, dev.index)
-    if key not in _SLOT_SHARD:      # logical shard of every (rank, slot); padding slots carry count 0
+    key = (w, n_shards, n, dev.index)
+    if key not in _SLOT_SHARD:      # buffers + the logical shard of every (rank, slot); padding slots keep count 0 for ever
         ids = []
         for r in range(w):
             sh = shards_for_rank(r, w, n_shards)
             ids += sh + [0] * (slots - len(sh))
-        _SLOT_SHARD[key] = (torch.tensor(ids, dtype=torch.int32, device=dev), ids)
-    slot_shard, ids = _SLOT_SHARD[key]
-    ev = fe = 0
-    overflowed = False
-    if token is not None:
-        st, overflowed = eng.pool_read_stats(token)
-        ev, fe = sum(int(x.evaluated) for x in st), sum(int(x.feasible) for x in st)
-    t = torch.tensor([ev, fe, 1 if overflowed else 0], dtype=torch.int64, device=dev)
-    dispatch.COPIED["h2d"] += 24
-    dist.all_reduce(t)
-    t_h = dispatch._d2h(t)
-    if int(t_h[2]) > 0:
+        _SLOT_SHARD[key] = (torch.tensor(ids, dtype=torch.int32, device=dev), ids,
+                            torch.zeros((slots, cap + 1, REC_W), dtype=torch.int32, device=dev),
+                            torch.empty((w * slots, cap + 1, REC_W), dtype=torch.int32, device=dev))
+    slot_shard, ids, blocks, all_blocks = _SLOT_SHARD[key]
+    if mine:
+        eng.pool_find_shards_headed(dem_d, dist_d, pool_size, mine[0], len(mine), n_shards, out=blocks[: len(mine)])
+    dist.all_gather_into_tensor(all_blocks, blocks)
+    plans, counts, ev, fe = eng.pool_merge_headed_packed(all_blocks, slot_shard, n, pool_size)
+    if int(counts.min()) < 0:
         return None
-    merged, mcnt = eng.pool_merge_padded(all_plans, all_counts, slot_shard, n, pool_size)
-    counts = dispatch._d2h(all_counts)
     kept = [0] * n_shards
     for r in range(w):
         for k_, sh in enumerate(shards_for_rank(r, w, n_shards)):
             kept[sh] = int(counts[r * slots + k_])
-    m = dispatch._d2h_int(mcnt)
-    return dispatch._d2h(merged[:m]), {"evaluated": int(t_h[0]), "feasible": int(t_h[1]), "kept_per_shard": kept, "kept": m}
+    return plans, {"evaluated": int(ev.sum()), "feasible": int(fe.sum()), "kept_per_shard": kept, "kept": len(plans)}
 
 
 def find_pool_sharded(demand, dist_table, pool_size: int, n_shards: int = REF_SHARDS,

@@ -15,6 +15,20 @@ def test_demand_csv_matches_reference_input_format():
     assert all(len(line) < 39 for line in txt.splitlines())   # pool_n.c:33 char line[40]
 
 
+def test_demand_csv_read_demand_quirks():
+    """readDemand (pool_n.c:30-54) read literally: a blank line is a record of zeros, missing fields stay zero, records
+    the file does not reach stay zero (the search still runs over `rec-number` customers), atoi swallows junk, and a
+    line longer than the 40-byte fgets buffer spills into the next record."""
+    txt = "0,5,7,3,1\n\n2,9\nx,4,-6,+2,1abc,99\n"
+    got = formats.read_demand_csv(txt, 6, pad_to=6)
+    assert got.tolist() == [[0, 5, 7, 3, 1], [0, 0, 0, 0, 0], [2, 9, 0, 0, 0], [0, 4, -6, 2, 1], [0, 0, 0, 0, 0], [0, 0, 0, 0, 0]]
+    assert formats.read_demand_csv(txt, 2).tolist() == [[0, 5, 7, 3, 1], [0, 0, 0, 0, 0]]          # linesNumb stops the loop
+    long_line = "1," + "0" * 40 + "7,8,9,10\n3,4,5,6,7\n"
+    got = formats.read_demand_csv(long_line)
+    assert got[0, 0] == 1 and len(got) == 3 and got[2].tolist() == [3, 4, 5, 6, 7]                  # first 39 bytes, the rest, next line
+    assert formats.read_demand_csv("", pad_to=3).tolist() == [[0] * 5] * 3
+
+
 def test_result_csv_round_trip():
     case = load_golden("pool_small.json")[5]
     k = case["pool_size"]

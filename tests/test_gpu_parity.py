@@ -628,6 +628,44 @@ def test_pool_1200_customers_golden_single_pass_and_windows(td):
     assert st[0].passes > 1
 
 
+def test_pool_headed_blocks_and_steady_state_path(td):
+    """Headed blocks (survivors + count + counters in one buffer, the layout of the multi-GPU gather) and the merge on
+    them: identical to the plain entry points, on config 3 and on a K = 2 / K = 3 case; find_pool_all takes the headed
+    steady-state path from its second call on and must keep returning the golden result and the reference's counters."""
+    import torch
+    gold = load_golden("pool722.json")
+    eng = td.engine()
+    dem_np, dist_np = g.pool_demand(), g.stand_distances(50)
+    for rep in range(3):
+        merged, st = td.find_pool_all(dem_np, dist_np, 4)
+        assert merged.tolist() == gold["merged"], rep
+        assert st["evaluated"] == sum(g.POOL722_EVALUATED) and st["feasible"] == sum(g.POOL722_FEASIBLE)
+        assert st["kept_per_shard"] == g.POOL722_KEPT and st["kept"] == 110
+    dem, dist = torch.from_numpy(dem_np).cuda(), torch.from_numpy(dist_np).cuda()
+    cap = 722 // 2 + 1
+    # two "ranks" with 5 + 3 shards, padded to 5 slots each, gathered in rank order: the multi-GPU layout on one device
+    slots = 5
+    all_blocks = torch.zeros((2 * slots, cap + 1, 9), dtype=torch.int32, device="cuda")
+    eng.pool_find_shards(dem, dist, 4, 0, 5, 8)                                  # sizes the record list for 5 shards
+    eng.pool_find_shards_headed(dem, dist, 4, 0, 5, 8, out=all_blocks[0:5])
+    eng.pool_find_shards(dem, dist, 4, 5, 3, 8)
+    eng.pool_find_shards_headed(dem, dist, 4, 5, 3, 8, out=all_blocks[5:8])
+    slot_shard = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7, 0, 0], dtype=torch.int32, device="cuda")
+    plans, counts, ev, fe = eng.pool_merge_headed_packed(all_blocks, slot_shard, 722, 4)
+    assert plans.tolist() == gold["merged"]
+    assert counts.tolist() == g.POOL722_KEPT + [0, 0]
+    assert ev.tolist()[:8] == g.POOL722_EVALUATED and fe.tolist()[:8] == g.POOL722_FEASIBLE
+    for s_ in range(8):
+        assert all_blocks[s_, 1: 1 + int(counts[s_])].cpu().numpy().tolist() == gold["shards"][s_]["plans"]
+    # small ragged case, every pool size (K < 4 keeps the reference's concatenation-order quirk in the merge)
+    case = load_golden("pool_small.json")
+    for c in case[6:12]:
+        d_np = np.array(c["demand"], dtype=np.int32)
+        for rep in range(2):
+            merged, st = td.find_pool_all(d_np, g.stand_distances(c["n_stands"]), c["pool_size"])
+            assert merged.tolist() == c["merged"], (c["label"], rep)
+
+
 def test_pool_async_overflow_reports_minus_one_and_recovers(td):
     """The asynchronous single pass (stats == NULL) cannot fall back to cost windows: when the record list is too small
     every count comes back as -1, nothing is read or written out of bounds (the selection does not run), and the
