@@ -88,17 +88,13 @@ int td_cost_matrix(const int32_t *dist, int n_stands,
 
 /* Rows [row_begin, row_begin + row_count) of the same matrix, written to a row_count x n buffer: the multi-GPU path
  * builds contiguous cab-row blocks per device (the loop of split.py:129-134 / Simulator.java:503-511 has no carried
- * state, so rows split trivially).  workspace is optional (NULL: none): with td_cost_matrix_workspace_bytes() of
- * scratch, big blocks take the grouped path -- rows of cabs standing at the same stand are identical, each distinct row
- * is gathered once and streamed to all of them. */
-size_t td_cost_matrix_workspace_bytes(int n_stands, int row_count);
+ * state, so rows split trivially). */
 int td_cost_matrix_rows(const int32_t *dist, int n_stands,
                         const int32_t *cab_to, int n_cabs,
                         const int32_t *cust_from, int n_cust,
                         int32_t fill, int32_t cutoff /* < 0: none */,
                         int row_begin, int row_count,
-                        int32_t *cost_out /* row_count*n */,
-                        void *workspace /* may be NULL */, size_t workspace_bytes, void *stream);
+                        int32_t *cost_out /* row_count*n */, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  LCM greedy             replaces LCM(...) in heuristic.py:24-33, split.py:161-175,

@@ -64,9 +64,7 @@ _SIGNATURES = {
     "td_prof_reset": (None, []),
     "td_prof_read": (_I, [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "td_cost_matrix": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp]),
-    "td_cost_matrix_workspace_bytes": (ctypes.c_size_t, [_I, _I]),
-    "td_cost_matrix_rows": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, _I, _I, c_vp, c_vp,
-                                ctypes.c_size_t, c_vp]),
+    "td_cost_matrix_rows": (_I, [c_vp, _I, c_vp, _I, c_vp, _I, ctypes.c_int32, ctypes.c_int32, _I, _I, c_vp, c_vp]),
     "td_lcm_workspace_bytes": (ctypes.c_size_t, [_I]),
     "td_lcm": (_I, [c_vp, _I, ctypes.POINTER(LcmParams), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "td_assign_workspace_bytes": (ctypes.c_size_t, [_I]),

@@ -119,11 +119,8 @@ class Engine:
         lo, hi = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
         if out is None:
             out = torch.empty((hi - lo, n), dtype=torch.int32, device=self.device)
-        nbytes = self.lib.td_cost_matrix_workspace_bytes(n_stands, hi - lo) if (hi - lo) * n >= (1 << 24) else 0
-        ws = self._workspace("cost", nbytes) if nbytes else None
         rc = self.lib.td_cost_matrix_rows(_ptr(dist), n_stands, _ptr(cab_to), n_cabs, _ptr(cust_from), n_cust, int(fill),
-                                          -1 if cutoff is None else int(cutoff), lo, hi - lo, _ptr(out), _ptr(ws),
-                                          ws.numel() if ws is not None else 0, _stream())
+                                          -1 if cutoff is None else int(cutoff), lo, hi - lo, _ptr(out), _stream())
         check(rc, "td_cost_matrix_rows")
         return out
 

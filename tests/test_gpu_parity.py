@@ -61,10 +61,10 @@ def test_cost_matrix_full_size_properties(td):
     assert np.array_equal(got, np.abs(cab_to[rows][:, None] - cust_from[None, :]))
 
 
-def test_cost_matrix_row_blocks_and_grouped_path(td):
-    """Row blocks (the multi-GPU split of split.py:129-134) concatenate to the whole matrix, on the row-at-a-time kernel
-    and on the grouped kernel (rows bucketed by cab stand; taken for blocks >= 2^24 cells), with dummy rows, dummy
-    columns, the cutoff, an asymmetric table and n % 4 != 0 (grouped path declined)."""
+def test_cost_matrix_row_blocks(td):
+    """Row blocks (the multi-GPU split of split.py:129-134) concatenate to the whole matrix: dummy rows, dummy columns,
+    the cutoff, an asymmetric table, n % 4 != 0 (scalar head / tail of every row) and blocks that start inside the
+    dummy rows."""
     import torch
     from taxidispatcher_b200 import parallel as P
     eng = td.engine()
@@ -85,7 +85,7 @@ def test_cost_matrix_row_blocks_and_grouped_path(td):
         for w in (2, 3):
             parts = [eng.cost_matrix(dd, dc, du, cutoff=cutoff, rows=P.rows_for_rank(n, r, w)).cpu().numpy() for r in range(w)]
             assert np.array_equal(np.concatenate(parts, axis=0), ref), (n_cabs, n_cust, S, w)
-    # the north-star shape through the public sharded entry point (one rank here: the whole matrix, grouped path)
+    # the north-star shape through the public sharded entry point (one rank here: the whole matrix)
     cab_to, cust_from = g.config5b()
     n, (lo, hi), block = P.cost_matrix_sharded(g.stand_distances(4000), cab_to, cust_from)
     assert (n, lo, hi) == (20000, 0, 20000)
