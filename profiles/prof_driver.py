@@ -32,6 +32,11 @@ if "pool8" in which:   # the launch bench.py times at N = 1: all 8 logical shard
     out, cnt, tok = eng.pool_find_shards(dem, dist, 4, 0, 8, 8, defer_stats=True)
     st2, ov = eng.pool_read_stats(tok)
     print("pool8 async", sum(s.evaluated for s in st2), "overflow", ov)
+if "pool5k" in which:   # north-star size: one 512-way slice (10 leading customers) of the 5000-customer input, single pass
+    dem = torch.from_numpy(g.pool_demand(5000, seed=5000)).cuda()
+    dist = torch.from_numpy(g.stand_distances(50)).cuda()
+    out, cnt, st = eng.pool_find_shards(dem, dist, 4, 255, 1, 512, max_feasible=120_000_000)
+    print("pool5k slice 255", st[0].evaluated, st[0].feasible, st[0].kept, "passes", st[0].passes)
 if "cost" in which:
     cab_to, cust_from = g.config5b()
     d = torch.from_numpy(g.stand_distances(4000)).cuda()

@@ -50,6 +50,10 @@ namespace td {
 
 constexpr int kTbl = 64;          // budget table entries per stand
 constexpr int kEnumThreads = 256;
+constexpr int kEnumThreadsWide = 768;   // one CTA per SM (big staged tables): 24 warps instead of 8
+constexpr int kIoffSmem = 2048;          // leaders whose item offsets are staged in shared memory
+constexpr size_t kEnumIoffBytes = (size_t(kIoffSmem) + 4) * 4;
+constexpr size_t kEnumWarpBytes = 256 * 4 + 2 * 32 * 16 + 64 * 8;   // histogram + staging A, B + tuple queue
 constexpr int kChunk = 128;       // records reserved per atomic
 constexpr int kSelThreads = 512;
 constexpr int kCustBits = 14;     // TD_POOL_MAX_CUSTOMERS = 16384
@@ -104,8 +108,9 @@ __device__ __forceinline__ void split_rank(unsigned long long r, int p[4], int &
 }
 
 // ---- prep ----------------------------------------------------------------------------------------
+__device__ __forceinline__ int4 scale_cust_rt(int4 c, int sh);
 __global__ void pool_prep_cust_kernel(const int32_t *__restrict__ demand, int n, const int32_t *__restrict__ dist,
-                                      int S, int4 *cust, PoolCtrl *ctrl) {
+                                      int S, int4 *cust, int4 *cust_s, int sh, PoolCtrl *ctrl) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     int f = demand[c * 5 + 1], t = demand[c * 5 + 2];
@@ -123,6 +128,7 @@ __global__ void pool_prep_cust_kernel(const int32_t *__restrict__ demand, int n,
     else if (fl < -2147483647.0) thr = INT_MIN;
     else thr = int(fl);
     cust[c] = make_int4(f, t, thr, w);
+    cust_s[c] = scale_cust_rt(make_int4(f, t, thr, w), sh);   // the enumeration's staged copy (fixed point of its evaluation)
 }
 
 // one CTA per stand: counting sort of the customers reachable from this stand by slack, descending
@@ -194,11 +200,12 @@ pool_item_offsets_kernel(const int4 *__restrict__ cust, const int32_t *__restric
 // the (cost << 5 | permutation) order key needs 5 legs < 2^26) is refused with TD_ERR_INVALID, never clamped.
 constexpr int kDistLimit = 1 << 22;
 __global__ void __launch_bounds__(256)
-pool_check_table_kernel(const int32_t *__restrict__ dist, long long cells, PoolCtrl *ctrl) {
+pool_check_table_kernel(const int32_t *__restrict__ dist, long long cells, PoolCtrl *ctrl, int32_t *dist_s, int sh) {
     int bad = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
         const int v = dist[i];
         bad |= (v < 0) | (v > kDistLimit);
+        if (dist_s) dist_s[i] = v << sh;       // the copy the enumeration stages by bulk copy (small tables only)
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) ctrl->bad_input = 1;
 }
@@ -212,7 +219,7 @@ pool_check_table_kernel(const int32_t *__restrict__ dist, long long cells, PoolC
 // On metric tables (|i-j|, pool_n.c:179-185) D* == D.  A table with a negative entry switches the bound off.
 constexpr int kPfMaxStands = 128;
 __global__ void __launch_bounds__(1024)
-pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict__ dclose, PoolCtrl *ctrl) {
+pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict__ dclose, int sh, PoolCtrl *ctrl) {
     extern __shared__ int32_t s_d[];
     const int cells = S * S;
     int neg = 0;
@@ -232,13 +239,14 @@ pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < cells; i += blockDim.x) dclose[i] = s_d[i];
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) dclose[i] = (s_d[i] > kDistLimit ? kDistLimit : s_d[i]) << sh;   // D* <= D <= limit on accepted tables
     if (threadIdx.x == 0) ctrl->closure_ok = neg ? 0u : 1u;
 }
 
 // ---- enumeration ---------------------------------------------------------------------------------
 struct EnumArgs {
-    const int4 *cust; const int32_t *dist; const int32_t *dclose; const int32_t *list; const int32_t *slack; const int32_t *cnt;
+    // cust_s, dist_s, dclose: copies in the fixed point of the evaluation (staged by bulk copy)
+    const int4 *cust; const int4 *cust_s; const int32_t *dist; const int32_t *dist_s; const int32_t *dclose; const int32_t *list; const int32_t *slack; const int32_t *cnt;
     const unsigned int *item_off; PoolRec *recs; PoolCtrl *ctrl;
     int n, S, start, stop; unsigned int cap;
     int step, shard_begin;        // leader p0 belongs to call slot p0 / step - shard_begin
@@ -266,6 +274,14 @@ __device__ __forceinline__ int4 scale_cust(int4 c) {
         const int lim = 1 << 25;
         const int z = c.z > lim ? lim : (c.z < -lim ? -lim : c.z);
         c.z = (z << SH) | ((1 << SH) - 1);
+    }
+    return c;
+}
+__device__ __forceinline__ int4 scale_cust_rt(int4 c, int sh) {
+    if (sh > 0) {
+        const int lim = 1 << 25;
+        const int z = c.z > lim ? lim : (c.z < -lim ? -lim : c.z);
+        c.z = (z << sh) | ((1 << sh) - 1);
     }
     return c;
 }
@@ -322,7 +338,6 @@ __device__ __forceinline__ void emit_records(const EnumArgs &a, WarpOut &wo, boo
 // 32 * slack + 31, and a leaf's key is  32 * (drop legs) + permutation index  -- ONE three-input add per leaf gives both the
 // last partial sum and the (cost, permutation) order key, and  key <= sl  is exactly  legs <= slack  because the index is
 // below 32.  e[i] = D(F3,T_i); t[i][j] = D(T_i,T_j); sl[i] from thr_i - (pickup legs from i to the last pickup).
-constexpr int kIoffSmem = 2048;    // leaders whose item offsets are staged in shared memory
 constexpr int kSh4 = 5;
 __device__ __forceinline__ void eval4s(const int e[4], const int t[4][4], const int sl[4], int &nfeas, int &best) {
     nfeas = 0; best = INT_MAX;
@@ -376,8 +391,10 @@ __device__ __forceinline__ void eval3(const int e[3], const int t[3][3], const i
 
 // kPF (K = 4 with the stand table in shared memory): the closure D* is staged next to the table and the lower bound of
 // pool_closure_kernel prunes pickup prefixes at the third and at the last pickup level.
-template <int K, bool kDistSmem, bool kCustSmem, bool kPF>
-__global__ void __launch_bounds__(kEnumThreads)
+// kThr: threads per CTA.  256 when several CTAs fit an SM; when the staged tables leave room for ONE CTA only (5000 customers:
+// 80 KB of customer records), a 768-thread CTA keeps 24 warps per SM busy instead of 8 (ncu r02n: 11 % warps active, 40 % issue).
+template <int K, bool kDistSmem, bool kCustSmem, bool kPF, int kThr>
+__global__ void __launch_bounds__(kThr)
 pool_enum_kernel(EnumArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t dist_b = (size_t(a.S) * a.S * 4 + 15) & ~size_t(15);
@@ -386,18 +403,43 @@ pool_enum_kernel(EnumArgs a) {
     int4 *s_cust = reinterpret_cast<int4 *>(smem_raw + (kDistSmem ? dist_b : 0) + (kPF ? dist_b : 0));
     constexpr int SH = (K == 4) ? kSh4 : 0;   // fixed-point shift of the K = 4 evaluation (eval4s)
     if (a.ctrl->bad_input) return;   // refused input (pool_prep_cust / pool_check_table): uniform, set before this launch
-    if (kDistSmem)
-        for (int i = threadIdx.x; i < a.S * a.S; i += kEnumThreads) {
-            s_dist[i] = a.dist[i] << SH;
-            if (kPF) s_dc[i] = a.dclose[i] << SH;      // D* <= D entry by entry
+    // The tables are staged by the TMA engine: the prep kernels left copies in the fixed point of the evaluation, one
+    // elected thread arms an mbarrier with the byte count and issues one 1-D bulk copy per table (cp.async.bulk,
+    // global -> shared, completion counted on the barrier); every thread then waits on the barrier's phase.
+    if (kDistSmem || kCustSmem) {
+        __shared__ __align__(8) unsigned long long s_mbar;
+        const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&s_mbar));
+        const unsigned cust_bytes = (unsigned(a.n) * 16u + 15u) & ~15u;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-    if (kCustSmem)
-        for (int i = threadIdx.x; i < a.n; i += kEnumThreads) s_cust[i] = scale_cust<SH>(a.cust[i]);
-    // item offsets per leader: searched once per work item, so keep them next to the tables when they fit
-    __shared__ unsigned s_ioff[kIoffSmem + 1];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned total = (kDistSmem ? unsigned(dist_b) : 0u) + (kPF ? unsigned(dist_b) : 0u) + (kCustSmem ? cust_bytes : 0u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+            auto bulk = [&](void *dst, const void *src, unsigned bytes) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst))), "l"(src), "r"(bytes), "r"(bar) : "memory");
+            };
+            if (kDistSmem) bulk(s_dist, a.dist_s, unsigned(dist_b));
+            if (kPF) bulk(s_dc, a.dclose, unsigned(dist_b));
+            if (kCustSmem) bulk(s_cust, a.cust_s, cust_bytes);
+        }
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    // everything else in shared memory is carved from the dynamic allocation too (a 768-thread CTA needs 68 KB of it, the
+    // static limit is 48 KB): item offsets per leader (searched once per work item), then per warp {cost histogram, batch
+    // staging A / B, tuple queue}
+    unsigned char *sm_rest = smem_raw + (kDistSmem ? dist_b : 0) + (kPF ? dist_b : 0) + (kCustSmem ? ((size_t(a.n) * 16 + 15) & ~size_t(15)) : 0);
+    unsigned *s_ioff = reinterpret_cast<unsigned *>(sm_rest);               // [kIoffSmem + 1]
+    unsigned char *sm_warp = sm_rest + kEnumIoffBytes + size_t(threadIdx.x >> 5) * kEnumWarpBytes;
     const bool ioff_smem = (a.stop - a.start) <= kIoffSmem;
     if (ioff_smem)
-        for (int i = threadIdx.x; i <= a.stop - a.start; i += kEnumThreads) s_ioff[i] = a.item_off[i];
+        for (int i = threadIdx.x; i <= a.stop - a.start; i += kThr) s_ioff[i] = a.item_off[i];
     const unsigned *ioff = ioff_smem ? s_ioff : a.item_off;
     __syncthreads();
     const DistView<kDistSmem, SH> D{kDistSmem ? s_dist : a.dist, a.S};
@@ -412,13 +454,12 @@ pool_enum_kernel(EnumArgs a) {
     unsigned long long my_eval = 0, my_feas = 0;
     int cur_slot = -1;
     WarpOut wo{0xffffffffu, unsigned(kChunk), false};
-    __shared__ unsigned s_hist[kEnumThreads / 32][kBuckets];   // per-warp cost histogram of the warp's current shard
-    unsigned *whist = s_hist[threadIdx.x >> 5];
+    unsigned *whist = reinterpret_cast<unsigned *>(sm_warp);            // [kBuckets] per-warp cost histogram of the warp's current shard
     // K = 4: per-warp staging of the current batch of third pickups {p2, F2, wait so far, slack of p0} / {slack of p1,
     // slack of p2, T2, end of its last-pickup range}, and the queue of pickup tuples that passed the bound
-    __shared__ int4 s_stA[K == 4 ? kEnumThreads / 32 : 1][32];
-    __shared__ int4 s_stB[K == 4 ? kEnumThreads / 32 : 1][32];
-    __shared__ unsigned long long s_queue[K == 4 ? kEnumThreads / 32 : 1][64];
+    int4 *stA = reinterpret_cast<int4 *>(sm_warp + kBuckets * 4);          // [32]
+    int4 *stB = stA + 32;                                                   // [32]
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(stB + 32);   // [64]
     for (int b = lane; b < kBuckets; b += 32) whist[b] = 0;
     __syncwarp();
     auto flush_counts = [&]() {
@@ -442,7 +483,6 @@ pool_enum_kernel(EnumArgs a) {
     };
 
     // ---- K = 4: queue of surviving pickup tuples; a full batch of 32 is evaluated at a time ----------------------
-    unsigned long long *queue = s_queue[K == 4 ? (threadIdx.x >> 5) : 0];
     int q_head = 0, q_cnt = 0;                        // warp-uniform ring state (64 entries, q_cnt < 32 between pushes)
     constexpr unsigned kCM = (1u << kCustBits) - 1;
     // all 24 drop-off orders of up to 32 queued tuples, one per lane; every tuple materialises its best feasible order
@@ -581,7 +621,6 @@ pool_enum_kernel(EnumArgs a) {
         // evaluated, one per lane (all 24 drop-off orders).  a01 and every D() below are in the x32 fixed point of eval4s.
         const int a01u = a01 >> SH;
         const int n2 = cand_count(a.cnt, c1.x, a01u);
-        int4 *stA = s_stA[K == 4 ? (threadIdx.x >> 5) : 0], *stB = s_stB[K == 4 ? (threadIdx.x >> 5) : 0];
         const unsigned long long ent01 = (((unsigned long long)unsigned(p0) << kCustBits) | unsigned(p1)) << (2 * kCustBits);
         unsigned my_tuples = 0;                        // valid pickup tuples seen by this lane (x 24 leaves each)
         for (int b2 = first_batch_only ? 0 : 32; b2 < (first_batch_only ? (n2 < 32 ? n2 : 32) : n2); b2 += 32) {
@@ -1312,7 +1351,7 @@ pool_pairs_emit_kernel(const PoolRec *__restrict__ kept, const PoolCtrl *ctrl, i
 }
 
 struct PoolWorkspace {
-    int4 *cust; int32_t *list, *slack, *cnt, *dclose; unsigned int *item_off; PoolRec *recs[2]; PoolRec *act[2]; PoolRec *kept;
+    int4 *cust, *cust_s; int32_t *list, *slack, *cnt, *dclose, *dist_s; unsigned int *item_off; PoolRec *recs[2]; PoolRec *act[2]; PoolRec *kept;
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolCtrl *ctrl; size_t bytes;
 };
 
@@ -1326,7 +1365,9 @@ static PoolWorkspace carve_pool(void *ws, int n, int S, int n_slots, int64_t max
     w.list = c.take<int32_t>(size_t(S) * nn);
     w.slack = c.take<int32_t>(size_t(S) * nn);
     w.cnt = c.take<int32_t>(size_t(S) * kTbl);
-    w.dclose = c.take<int32_t>(S <= kPfMaxStands ? size_t(S) * S : 1);
+    w.dclose = c.take<int32_t>(S <= kPfMaxStands ? size_t(S) * S + 4 : 1);   // + 4: bulk copies move whole 16-byte units
+    w.dist_s = c.take<int32_t>(S <= kPfMaxStands ? size_t(S) * S + 4 : 1);
+    w.cust_s = c.take<int4>(nn);
     w.item_off = c.take<unsigned int>(nn + 2);
     w.recs[0] = c.take<PoolRec>(size_t(max_records));
     w.recs[1] = c.take<PoolRec>(size_t(max_records));
@@ -1358,21 +1399,32 @@ static int launch_enum(const EnumArgs &a, int sms, bool closure, cudaStream_t st
     const bool ds = dist_b <= 64 * 1024;
     const bool pf = K == 4 && ds && closure;          // the closure table is staged next to the distance table
     const bool cs = cust_b <= (pf && dist_b > 32 * 1024 ? 48 * 1024 : 96 * 1024);
-    const size_t smem = (ds ? dist_b : 0) + (pf ? dist_b : 0) + (cs ? cust_b : 0);
+    const size_t tables = (ds ? dist_b : 0) + (pf ? dist_b : 0) + (cs ? ((cust_b + 15) & ~size_t(15)) : 0);
+#define TD_ENUM_LAUNCH(DS, CS, PF, THR)                                                                                  \
+    do {                                                                                                                 \
+        auto kern = pool_enum_kernel<K, DS, CS, PF, THR>;                                                                \
+        const size_t smem = tables + kEnumIoffBytes + size_t(THR / 32) * kEnumWarpBytes;                                 \
+        TD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(224 * 1024)));           \
+        TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THR, smem));                            \
+        if (per_sm < 1) return TD_ERR_CUDA;                                                                              \
+        if (THR == kEnumThreads && per_sm == 1 && K == 4 && !getenv("TD_ENUM_NARROW")) break;   /* take the wide CTA */ \
+        kern<<<sms * (per_sm > 4 ? 4 : per_sm), THR, smem, st>>>(a);   /* resident CTAs only: a CTA that starts     */ \
+        launched = true;                                                /* late finds the queue empty                */ \
+    } while (0)
 #define TD_ENUM_CASE(DS, CS, PF)                                                                                         \
     do {                                                                                                                 \
-        auto kern = pool_enum_kernel<K, DS, CS, PF>;                                                                     \
-        TD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(190 * 1024)));           \
         int per_sm = 0;                                                                                                  \
-        TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEnumThreads, smem));                   \
-        if (per_sm < 1) return TD_ERR_CUDA;                                                                              \
-        kern<<<sms * (per_sm > 4 ? 4 : per_sm), kEnumThreads, smem, st>>>(a);   /* resident CTAs only: a CTA that    */ \
-    } while (0)                                                                  /* starts late finds the queue empty */
+        bool launched = false;                                                                                           \
+        TD_ENUM_LAUNCH(DS, CS, PF, kEnumThreads);                                                                        \
+        if (!launched) TD_ENUM_LAUNCH(DS, CS, PF, (K == 4 ? kEnumThreadsWide : kEnumThreads));                           \
+        if (!launched) return TD_ERR_CUDA;                                                                               \
+    } while (0)
     if (pf) { if (cs) TD_ENUM_CASE(true, true, (K == 4)); else TD_ENUM_CASE(true, false, (K == 4)); }
     else if (ds && cs) TD_ENUM_CASE(true, true, false);
     else if (ds) TD_ENUM_CASE(true, false, false);
     else if (cs) TD_ENUM_CASE(false, true, false);
     else TD_ENUM_CASE(false, false, false);
+#undef TD_ENUM_LAUNCH
 #undef TD_ENUM_CASE
     TD_LAUNCH_CHECK();
     return TD_OK;
@@ -1444,7 +1496,8 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
     const int keep_cap = n / 2 + 1;
 
     TD_CUDA_TRY(cudaMemsetAsync(w.ctrl, 0, sizeof(PoolCtrl), st));
-    pool_prep_cust_kernel<<<(n + 255) / 256, 256, 0, st>>>(demand, n, dist, n_stands, w.cust, w.ctrl);
+    const int sh = pool_size == 4 ? kSh4 : 0;                                  // fixed point of the enumeration's evaluation
+    pool_prep_cust_kernel<<<(n + 255) / 256, 256, 0, st>>>(demand, n, dist, n_stands, w.cust, w.cust_s, sh, w.ctrl);
     TD_LAUNCH_CHECK();
     pool_build_lists_kernel<<<n_stands, 256, 0, st>>>(w.cust, n, dist, n_stands, w.list, w.slack, w.cnt);
     TD_LAUNCH_CHECK();
@@ -1454,14 +1507,14 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
         const long long cells = (long long)n_stands * n_stands;
         const long long want = (cells + 256 * 16 - 1) / (256 * 16);
         const int grid = int(want < 1 ? 1 : (want > 4LL * device_sm_count() ? 4LL * device_sm_count() : want));
-        pool_check_table_kernel<<<grid, 256, 0, st>>>(dist, cells, w.ctrl);
+        pool_check_table_kernel<<<grid, 256, 0, st>>>(dist, cells, w.ctrl, n_stands <= kPfMaxStands ? w.dist_s : nullptr, sh);
         TD_LAUNCH_CHECK();
     }
     const bool closure = pool_size == 4 && n_stands <= kPfMaxStands;
     if (closure) {
         const size_t cl_smem = size_t(n_stands) * n_stands * 4;
         TD_CUDA_TRY(cudaFuncSetAttribute(pool_closure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(64 * 1024)));
-        pool_closure_kernel<<<1, 1024, cl_smem, st>>>(dist, n_stands, w.dclose, w.ctrl);
+        pool_closure_kernel<<<1, 1024, cl_smem, st>>>(dist, n_stands, w.dclose, sh, w.ctrl);
         TD_LAUNCH_CHECK();
     }
 
@@ -1481,7 +1534,7 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
     };
     auto run_enum = [&](int cost_lo, int cost_hi, bool use_alive, bool count_stats, int stride) -> int {
         EnumArgs ea;
-        ea.cust = w.cust; ea.dist = dist; ea.dclose = w.dclose; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
+        ea.cust = w.cust; ea.cust_s = w.cust_s; ea.dist = dist; ea.dist_s = w.dist_s; ea.dclose = w.dclose; ea.list = w.list; ea.slack = w.slack; ea.cnt = w.cnt; ea.item_off = w.item_off;
         ea.recs = w.recs[0]; ea.ctrl = w.ctrl; ea.n = n; ea.S = n_stands; ea.start = start; ea.stop = stop;
         ea.cap = unsigned(rec_cap64); ea.step = step; ea.shard_begin = shard_begin;
         ea.cost_lo = cost_lo; ea.cost_hi = cost_hi; ea.alive = use_alive ? w.alive : nullptr;
