@@ -256,6 +256,7 @@ struct EnumArgs {
     const uint8_t *alive;         // [shard_count x n] or NULL (first pass: everybody is free)
     int count_stats;              // accumulate evaluated / feasible (first pass only)
     int item_stride;              // > 1: sampling pass -- every item_stride-th item, histogram only
+    unsigned int ioff_bytes;      // shared memory reserved for the staged item offsets (multiple of 16)
 };
 
 template <bool kDistSmem, int SH>
@@ -394,7 +395,7 @@ __device__ __forceinline__ void eval3(const int e[3], const int t[3][3], const i
 // kThr: threads per CTA.  256 when several CTAs fit an SM; when the staged tables leave room for ONE CTA only (5000 customers:
 // 80 KB of customer records), a 768-thread CTA keeps 24 warps per SM busy instead of 8 (ncu r02n: 11 % warps active, 40 % issue).
 template <int K, bool kDistSmem, bool kCustSmem, bool kPF, int kThr>
-__global__ void __launch_bounds__(kThr)
+__global__ void __launch_bounds__(kThr, kThr == 256 ? 4 : 1)   // 64 registers: four 256-thread CTAs (32 warps) per SM
 pool_enum_kernel(EnumArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t dist_b = (size_t(a.S) * a.S * 4 + 15) & ~size_t(15);
@@ -436,7 +437,7 @@ pool_enum_kernel(EnumArgs a) {
     // staging A / B, tuple queue}
     unsigned char *sm_rest = smem_raw + (kDistSmem ? dist_b : 0) + (kPF ? dist_b : 0) + (kCustSmem ? ((size_t(a.n) * 16 + 15) & ~size_t(15)) : 0);
     unsigned *s_ioff = reinterpret_cast<unsigned *>(sm_rest);               // [kIoffSmem + 1]
-    unsigned char *sm_warp = sm_rest + kEnumIoffBytes + size_t(threadIdx.x >> 5) * kEnumWarpBytes;
+    unsigned char *sm_warp = sm_rest + a.ioff_bytes + size_t(threadIdx.x >> 5) * kEnumWarpBytes;
     const bool ioff_smem = (a.stop - a.start) <= kIoffSmem;
     if (ioff_smem)
         for (int i = threadIdx.x; i <= a.stop - a.start; i += kThr) s_ioff[i] = a.item_off[i];
@@ -1393,17 +1394,19 @@ static int64_t record_slack() { return int64_t(kChunk) * 148 * 64; }
     } while (0)
 
 template <int K>
-static int launch_enum(const EnumArgs &a, int sms, bool closure, cudaStream_t st) {
+static int launch_enum(EnumArgs a, int sms, bool closure, cudaStream_t st) {
     const size_t dist_b = (size_t(a.S) * a.S * 4 + 15) & ~size_t(15);
     const size_t cust_b = size_t(a.n) * 16;
     const bool ds = dist_b <= 64 * 1024;
     const bool pf = K == 4 && ds && closure;          // the closure table is staged next to the distance table
     const bool cs = cust_b <= (pf && dist_b > 32 * 1024 ? 48 * 1024 : 96 * 1024);
     const size_t tables = (ds ? dist_b : 0) + (pf ? dist_b : 0) + (cs ? ((cust_b + 15) & ~size_t(15)) : 0);
+    const int n_lead = a.stop - a.start;
+    a.ioff_bytes = unsigned(((size_t(n_lead <= kIoffSmem ? n_lead : 0) + 1) * 4 + 15) & ~size_t(15));   // staged only when they fit
 #define TD_ENUM_LAUNCH(DS, CS, PF, THR)                                                                                  \
     do {                                                                                                                 \
         auto kern = pool_enum_kernel<K, DS, CS, PF, THR>;                                                                \
-        const size_t smem = tables + kEnumIoffBytes + size_t(THR / 32) * kEnumWarpBytes;                                 \
+        const size_t smem = tables + a.ioff_bytes + size_t(THR / 32) * kEnumWarpBytes;                                   \
         TD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(224 * 1024)));           \
         TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THR, smem));                            \
         if (per_sm < 1) return TD_ERR_CUDA;                                                                              \
