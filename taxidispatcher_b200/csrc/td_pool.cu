@@ -231,11 +231,15 @@ pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict
         s_d[i] = v;
     }
     neg = __syncthreads_or(neg);
+    // 32 x 32 thread tile over the table (no index division in the k loop); row k and column k do not change in step k
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int k = 0; k < S; ++k) {
-        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-            const int r = i / S, c = i - r * S;
-            const int via = s_d[r * S + k] + s_d[k * S + c];   // row k and column k do not change in step k
-            if (via < s_d[i]) s_d[i] = via;
+        for (int r = ty; r < S; r += 32) {
+            const int rk = s_d[r * S + k];
+            for (int c = tx; c < S; c += 32) {
+                const int via = rk + s_d[k * S + c];
+                if (via < s_d[r * S + c]) s_d[r * S + c] = via;
+            }
         }
         __syncthreads();
     }
@@ -711,6 +715,7 @@ struct SelArgs {
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolRec *kept;
     int n, K;
     int n_slots, step, shard_begin, keep_cap;   // per-slot state lives at [slot * n + customer]
+    unsigned int step_inv;                      // ceil(2^32 / step): p0 / step == umulhi(p0, step_inv) for p0, step <= 2^14 (p0 * step < 2^32)
     int first_pass;                             // 1: every customer starts free; 0: keep alive[] from the earlier windows
     int cost_hi;                                // records with cost >= cost_hi were counted in hist but not materialised
 };
@@ -804,7 +809,8 @@ pool_select_kernel(SelArgs a) {
     grid.sync();
     for (int i = threadIdx.x; i < a.n_slots * kMaxBands; i += blockDim.x) s_band_hi[i / kMaxBands][i % kMaxBands] = ctrl->band_hi[i / kMaxBands][i % kMaxBands];
     __syncthreads();
-    auto slot_of = [&](int p0) -> int { return p0 / a.step - a.shard_begin; };
+    // p0 / step without a division per record (step_inv == 0: step is 1)
+    auto slot_of = [&](int p0) -> int { return (a.step_inv ? int(__umulhi(unsigned(p0), a.step_inv)) : p0) - a.shard_begin; };
     // single-level keys when every materialised cost fits beside the repacked rank (uniform: from the histogram)
     int cb = 1;
     while ((1 << cb) < n) ++cb;
@@ -1090,10 +1096,10 @@ pool_emit_kernel(const PoolRec *__restrict__ kept_all, const PoolCtrl *ctrl, int
 constexpr int kMergeFast = 8192;
 __global__ void __launch_bounds__(1024)
 pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, const int32_t *__restrict__ counts, int cap,
-                  int headed, const int32_t *__restrict__ slot_shard, unsigned long long *ckey /* total */,
+                  int headed, int fast_cap, const int32_t *__restrict__ slot_shard, unsigned long long *ckey /* total */,
                   int32_t *crow /* total */, int32_t *order_key /* total */, int32_t *owner /* n */, uint8_t *state /* total */,
                   int32_t *plans_out, int32_t *n_plans_out) {
-    extern __shared__ __align__(16) unsigned char msm[];   // fast path: keys[kMergeFast] | rows[kMergeFast] | owner[n] | state[kMergeFast]
+    extern __shared__ __align__(16) unsigned char msm[];   // fast path: keys | rows | customers (4 x u16) [fast_cap each] | owner[n] | state[fast_cap]
     __shared__ int s_m, s_live;
     __shared__ unsigned long long tile[1024];
     __shared__ int s_scan[1024];
@@ -1126,10 +1132,11 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, 
     const int m = s_m;
     if (m == 0) { if (tid == 0) *n_plans_out = 0; return; }
 
-    if (m <= kMergeFast && n <= TD_POOL_MAX_CUSTOMERS) {
+    if (m <= fast_cap) {   // fast_cap: power of two, the arrays below hold that many rows (0: no fast path)
         unsigned long long *keys = reinterpret_cast<unsigned long long *>(msm);
-        int *rows = reinterpret_cast<int *>(msm + size_t(kMergeFast) * 8);
-        int *own = rows + kMergeFast;
+        int *rows = reinterpret_cast<int *>(msm + size_t(fast_cap) * 8);
+        ushort4 *cu = reinterpret_cast<ushort4 *>(rows + fast_cap);   // customers of the row at sorted position i (n <= 16384)
+        int *own = reinterpret_cast<int *>(cu + fast_cap);
         uint8_t *st = reinterpret_cast<uint8_t *>(own + n);
         int P = 1;
         while (P < m) P <<= 1;
@@ -1153,7 +1160,16 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, 
                 }
                 __syncthreads();
             }
-        for (int i = tid; i < m; i += blockDim.x) st[i] = 0;
+        for (int i = tid; i < m; i += blockDim.x) {
+            st[i] = 0;
+            const int32_t *row = row_ptr(rows[i]);
+            ushort4 c4 = make_ushort4(0, 0, 0, 0);
+            c4.x = (unsigned short)row[0]; c4.y = (unsigned short)row[1];
+            if (K > 2) c4.z = (unsigned short)row[2];
+            if (K > 3) c4.w = (unsigned short)row[3];
+            cu[i] = c4;
+        }
+        auto cust_of = [&](const ushort4 c4, int q) -> int { return q == 0 ? c4.x : q == 1 ? c4.y : q == 2 ? c4.z : c4.w; };
         for (;;) {   // dominance rounds: sorted position = scan rank
             for (int c = tid; c < n; c += blockDim.x) own[c] = INT_MAX;
             if (tid == 0) s_live = 0;
@@ -1161,30 +1177,30 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, 
             for (int i = tid; i < m; i += blockDim.x)
                 if (st[i] == 0) {
                     s_live = 1;
-                    const int32_t *row = row_ptr(rows[i]);
-                    for (int q = 0; q < K; ++q) atomicMin(&own[row[q]], i);
+                    const ushort4 c4 = cu[i];
+                    for (int q = 0; q < K; ++q) atomicMin(&own[cust_of(c4, q)], i);
                 }
             __syncthreads();
             if (!s_live) break;
             for (int i = tid; i < m; i += blockDim.x)
                 if (st[i] == 0) {
-                    const int32_t *row = row_ptr(rows[i]);
+                    const ushort4 c4 = cu[i];
                     bool dom = true;
-                    for (int q = 0; q < K; ++q) dom = dom && own[row[q]] == i;
+                    for (int q = 0; q < K; ++q) dom = dom && own[cust_of(c4, q)] == i;
                     if (dom) st[i] = 1;
                 }
             __syncthreads();
             for (int i = tid; i < m; i += blockDim.x)   // customers of kept plans are taken
                 if (st[i] == 1) {
-                    const int32_t *row = row_ptr(rows[i]);
-                    for (int q = 0; q < K; ++q) own[row[q]] = -1;
+                    const ushort4 c4 = cu[i];
+                    for (int q = 0; q < K; ++q) own[cust_of(c4, q)] = -1;
                 }
             __syncthreads();
             for (int i = tid; i < m; i += blockDim.x)
                 if (st[i] == 0) {
-                    const int32_t *row = row_ptr(rows[i]);
+                    const ushort4 c4 = cu[i];
                     bool hit = false;
-                    for (int q = 0; q < K; ++q) hit = hit || own[row[q]] == -1;
+                    for (int q = 0; q < K; ++q) hit = hit || own[cust_of(c4, q)] == -1;
                     if (hit) st[i] = 2;
                 }
             __syncthreads();
@@ -1552,6 +1568,7 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
         sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
         sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = pool_size;
         sa.n_slots = shard_count; sa.step = step; sa.shard_begin = shard_begin; sa.keep_cap = keep_cap;
+        sa.step_inv = step > 1 ? unsigned(((1ull << 32) + unsigned(step) - 1) / unsigned(step)) : 0u;
         sa.first_pass = first ? 1 : 0;
         sa.cost_hi = window_hi;
         void *sargs[] = {(void *)&sa};
@@ -1720,6 +1737,7 @@ extern "C" int td_pool_pairs(const int32_t *from, const int32_t *to, int n, cons
     sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
     sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = 2;
     sa.n_slots = 1; sa.step = n + 1; sa.shard_begin = 0; sa.keep_cap = n / 2 + 1; sa.first_pass = 1; sa.cost_hi = INT_MAX;
+    sa.step_inv = unsigned(((1ull << 32) + unsigned(n + 1) - 1) / unsigned(n + 1));   // n >= 2 here
     int per_sm = 0;
     TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_select_kernel, kSelThreads, 0));
     if (per_sm < 1) return TD_ERR_CUDA;
@@ -1758,9 +1776,14 @@ static int launch_merge(const int32_t *plans, int n_slots, int cap, int headed, 
                         int n, int pool_size, int32_t *plans_out, int32_t *n_plans_out, void *workspace, cudaStream_t st) {
     const int total = n_slots * cap;
     MergeWs w = carve_merge(workspace, total, n);
-    const size_t smem = n <= TD_POOL_MAX_CUSTOMERS ? size_t(kMergeFast) * 13 + size_t(n) * 4 + 16 : 0;   // keys + rows + state + owner
+    // fast path capacity: the largest power of two (<= kMergeFast) whose arrays fit beside the per-customer table
+    int fast_cap = 0;
+    if (n <= TD_POOL_MAX_CUSTOMERS)
+        for (fast_cap = kMergeFast; fast_cap >= 256 && size_t(fast_cap) * 21 + size_t(n) * 4 + 16 > 200 * 1024; fast_cap >>= 1) {}
+    if (fast_cap < 256) fast_cap = 0;
+    const size_t smem = fast_cap ? size_t(fast_cap) * 21 + size_t(n) * 4 + 16 : 0;   // keys + rows + customers + state + owner
     if (smem) TD_CUDA_TRY(cudaFuncSetAttribute(pool_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    pool_merge_kernel<<<1, 1024, smem, st>>>(plans, n_slots, n, pool_size, counts, cap, headed, slot_shard, w.ckey, w.crow,
+    pool_merge_kernel<<<1, 1024, smem, st>>>(plans, n_slots, n, pool_size, counts, cap, headed, fast_cap, slot_shard, w.ckey, w.crow,
                                              w.order_key, w.owner, w.state, plans_out, n_plans_out);
     TD_LAUNCH_CHECK();
     return TD_OK;
