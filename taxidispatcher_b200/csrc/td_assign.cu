@@ -980,6 +980,161 @@ assign_kernel(AsgArgs a) {
     if (tid == 0) *a.objective_out = failed ? LLONG_MIN : ctrl->objective;
 }
 
+// ---- small instances: one CTA, everything in shared memory ------------------------------------------------------------
+// BASELINE config 1 (200 x 200, python.py:6-25) spends its time in grid barriers when it runs through assign_kernel
+// (0.68 ms for a 160 KB matrix).  Up to kSmallN rows the whole matrix fits the shared memory of ONE SM: a single CTA runs
+// the classic primal-dual shortest-augmenting-path method (Kuhn-Munkres with potentials; column j lives in thread j's
+// registers: its minimum reduced cost, predecessor, potential and visited flag), so a path step costs three block
+// barriers and one block-wide arg-min instead of two grid-wide barriers.  Start: row minima, column minima of the
+// row-reduced costs, greedy matching on tight cells -- only the rows that stay free are augmented.
+// Exact for any int32 costs (potentials and distances in int64); ties resolve to the smallest column, deterministic.
+// Leaves the dual potentials in the workspace like assign_kernel does (td_assign_read_duals / td_assign_certify).
+constexpr int kSmallN = 232;          // 232^2 * 4 B = 210 KB of the 227 KB
+constexpr int kSmallThreads = 256;
+__global__ void __launch_bounds__(kSmallThreads)
+assign_small_kernel(const int32_t *__restrict__ cost, int n, int32_t *col_of_row_out, long long *objective_out, uint8_t *x_out,
+                    long long *u_out, long long *v_out, AsgCtrl *ctrl) {
+    extern __shared__ __align__(16) unsigned char ssm[];
+    int32_t *c = reinterpret_cast<int32_t *>(ssm);                                   // [n][n]
+    long long *u = reinterpret_cast<long long *>(ssm + ((size_t(n) * n * 4 + 15) & ~size_t(15)));   // [n]
+    int *p = reinterpret_cast<int *>(u + n);        // p[j]: row matched to column j, -1: free       [n]
+    int *way = p + n;                               // predecessor column on the alternating path, -1: the root   [n]
+    int *mate = way + n;                            // mate[i]: column of row i, -1: free            [n]
+    __shared__ long long s_rk[kSmallThreads / 32];
+    __shared__ int s_rj[kSmallThreads / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const long long kInf = LLONG_MAX / 4;
+    for (int i = t; i < n * n; i += kSmallThreads) c[i] = __ldg(cost + i);
+    __syncthreads();
+    // row minima -> u; column minima of the row-reduced costs -> v (thread j owns column j)
+    if (t < n) {
+        int m = INT_MAX;
+        for (int j = 0; j < n; ++j) { const int v0 = c[t * n + ((j + t) % n)]; m = v0 < m ? v0 : m; }   // rotated: spreads the banks
+        u[t] = m;
+        p[t] = -1; mate[t] = -1;
+    }
+    __syncthreads();
+    long long v = 0;
+    if (t < n) {
+        long long m = kInf;
+        for (int i = 0; i < n; ++i) { const long long r = (long long)c[i * n + t] - u[i]; m = r < m ? r : m; }
+        v = m;
+    }
+    // greedy matching on tight cells: every free column asks for the lowest free row that is tight with it, every asked
+    // row accepts the lowest such column
+    __shared__ int s_progress;
+    for (int round = 0; round < 4; ++round) {   // more rounds cost more than the few pairs they add (measured)
+        __syncthreads();
+        if (t == 0) s_progress = 0;
+        int pick = -1;
+        if (t < n && p[t] < 0)
+            for (int i = 0; i < n && pick < 0; ++i)
+                if (mate[i] < 0 && (long long)c[i * n + t] - u[i] - v == 0) pick = i;
+        if (t < n) way[t] = pick;                // several columns may ask for the same row
+        __syncthreads();
+        if (t < n && mate[t] < 0) {
+            int got = -1;
+            for (int j = 0; j < n && got < 0; ++j)
+                if (way[j] == t) got = j;
+            if (got >= 0) { mate[t] = got; p[got] = t; s_progress = 1; }
+        }
+        __syncthreads();
+        if (!s_progress) break;
+    }
+    __syncthreads();
+    // ---- augment every row that is still free ---------------------------------------------------------------------
+    // Dijkstra over the columns from row i, one DISTANCE LEVEL per step: every unvisited column at the current minimum
+    // joins the tree together and the rows matched to them are relaxed in the same step (on the reference's degenerate
+    // costs a level holds dozens of columns; one column per step took 2.6x longer than the cooperative kernel).
+    int *rows_new = mate + n;                    // rows whose edges are relaxed in this step                     [n]
+    __shared__ int s_nnew, s_jfree, s_wcnt[kSmallThreads / 32];
+    for (int i = 0; i < n; ++i) {
+        if (mate[i] >= 0) continue;              // uniform: mate[] is in shared memory, read after a barrier
+        long long minv = kInf;                   // column t: best reduced distance so far
+        bool used = false;                       // column t is in the tree
+        if (t < n) way[t] = -1;
+        if (t == 0) { rows_new[0] = i; s_nnew = 1; }
+        __syncthreads();
+        int jend;
+        for (;;) {
+            // relax the rows that joined in the previous step (list order = column order: deterministic predecessors)
+            const int nnew = s_nnew;
+            long long key = kInf;
+            if (t < n && !used) {
+                for (int k = 0; k < nnew; ++k) {
+                    const int r = rows_new[k];
+                    const long long cur = (long long)c[r * n + t] - u[r] - v;
+                    if (cur < minv) { minv = cur; way[t] = r == i ? -1 : mate[r]; }
+                }
+                key = minv;
+            }
+            // block minimum of the distances of the unvisited columns
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(0xffffffffu, key, o); key = ok < key ? ok : key; }
+            if (lane == 0) s_rk[w] = key;
+            __syncthreads();                     // (also: everybody has read s_nnew / rows_new)
+            long long delta = s_rk[0];
+#pragma unroll
+            for (int k = 1; k < kSmallThreads / 32; ++k) delta = s_rk[k] < delta ? s_rk[k] : delta;
+            // dual update: tree rows up, tree columns down, the other columns come closer
+            const bool joins = t < n && !used && minv == delta;
+            if (t < n) {
+                if (used) { u[p[t]] += delta; v -= delta; }
+                else minv -= delta;
+            }
+            if (t == 0) { u[i] += delta; s_jfree = INT_MAX; }
+            // the columns at the minimum join the tree; their rows form the next list (positions by block prefix)
+            const unsigned ball = __ballot_sync(0xffffffffu, joins && p[t] >= 0);
+            if (lane == 0) s_wcnt[w] = __popc(ball);
+            __syncthreads();                     // u[] settled, s_jfree reset, warp counts published
+            if (joins) {
+                used = true;
+                if (p[t] < 0) atomicMin(&s_jfree, t);
+                else {
+                    int pos = __popc(ball & ((1u << lane) - 1));
+                    for (int k = 0; k < w; ++k) pos += s_wcnt[k];
+                    rows_new[pos] = p[t];
+                }
+            }
+            if (t == 0) { int tot = 0; for (int k = 0; k < kSmallThreads / 32; ++k) tot += s_wcnt[k]; s_nnew = tot; }
+            __syncthreads();
+            if (s_jfree != INT_MAX) { jend = s_jfree; break; }   // a free column at this level: augment (smallest one)
+        }
+        // flip the alternating path (thread 0; a handful of steps)
+        if (t == 0) {
+            int j = jend;
+            for (;;) {
+                const int jp = way[j];
+                const int r = jp < 0 ? i : p[jp];
+                p[j] = r; mate[r] = j;
+                if (jp < 0) break;
+                j = jp;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- results ------------------------------------------------------------------------------------------------------
+    long long part = 0;
+    if (t < n) {
+        const int j = mate[t];
+        col_of_row_out[t] = j;
+        part = c[t * n + j];
+        if (x_out) x_out[size_t(t) * n + j] = 1;
+        u_out[t] = u[t];
+        v_out[t] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_rk[w] = part;
+    __syncthreads();
+    if (t == 0) {
+        long long tot = 0;
+        for (int k = 0; k < kSmallThreads / 32; ++k) tot += s_rk[k];
+        *objective_out = tot;
+        ctrl->objective = tot; ctrl->status = TD_OK; ctrl->phases = 1;
+    }
+}
+
 static AsgArgs carve_assign(void *ws, int n, size_t *bytes) {
     Carver c(ws);
     AsgArgs a;
@@ -1109,6 +1264,24 @@ static int td::assign_run(const int32_t *cost, int n, int nr, int32_t *col_of_ro
     if (const char *e = getenv("TD_ASSIGN_CARRY_MIN")) a.carry_min_levels = atoi(e);
     TD_CUDA_TRY(cudaMemsetAsync(a.ctrl, 0, sizeof(AsgCtrl), st));
     if (x_out) TD_CUDA_TRY(cudaMemsetAsync(x_out, 0, size_t(n) * n, st));
+    if (n <= kSmallN && nr == n && !getenv("TD_ASSIGN_NO_SMALL")) {   // balanced and small: one CTA in shared memory
+        const size_t smem = ((size_t(n) * n * 4 + 15) & ~size_t(15)) + size_t(n) * (8 + 4 + 4 + 4 + 4) + 64;
+        TD_CUDA_TRY(cudaFuncSetAttribute(assign_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        {
+            ProfScope prof(TD_PROF_ASSIGN, st);
+            assign_small_kernel<<<1, kSmallThreads, smem, st>>>(cost, n, col_of_row_out, a.objective_out, x_out, a.u, a.v, a.ctrl);
+        }
+        TD_LAUNCH_CHECK();
+        if (stats) {
+            AsgCtrl h;
+            TD_CUDA_TRY(cudaMemcpyAsync(&h, a.ctrl, sizeof h, cudaMemcpyDeviceToHost, st));
+            TD_CUDA_TRY(cudaStreamSynchronize(st));
+            stats->objective = h.objective;
+            stats->rows_scanned = n;          // the matrix is read from HBM once
+            stats->phases = 1;
+        }
+        return TD_OK;
+    }
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(cost) & 15) == 0);
     void *kern = vec ? (void *)assign_kernel<true> : (void *)assign_kernel<false>;
     int per_sm = 0;

@@ -359,6 +359,28 @@ def test_assign_large_magnitudes_take_the_64_bit_sweeps(td, n):
     _check_assign(td, c)
 
 
+def test_assign_small_instances_both_kernels(td, monkeypatch):
+    """n <= 232 balanced instances run in one CTA (assign_small_kernel, everything in shared memory); the cooperative
+    kernel must keep solving them too (TD_ASSIGN_NO_SMALL=1).  Objective vs scipy, permutation, and the dual certificate
+    of either kernel, on degenerate (U[0,2]), uniform, negative and 2^30-magnitude costs and on the KATs."""
+    rng = np.random.default_rng(88)
+    cases = [np.array([5, 5, 0, 5, 1, 1, 3, 8, 9, 9, 5, 0, 100, 100, 100, 100]).reshape(4, 4), g.config1a()]
+    for n in (1, 2, 3, 7, 33, 100, 199, 232):
+        cases.append(rng.integers(0, 3, (n, n)))
+        cases.append(rng.integers(-1000, 1000, (n, n)))
+    cases.append(rng.integers(0, 1 << 30, (150, 150)))
+    cases.append(np.full((50, 50), 7))
+    for no_small in ("", "1"):
+        if no_small:
+            monkeypatch.setenv("TD_ASSIGN_NO_SMALL", "1")
+        for M in cases:
+            M = np.ascontiguousarray(M, dtype=np.int32)
+            _check_assign(td, M)
+            obj, col, u, v, cert = _certify(td, M)
+            assert cert["optimal"] and obj == cert["dual_objective"], (no_small, M.shape, cert)
+    monkeypatch.delenv("TD_ASSIGN_NO_SMALL", raising=False)
+
+
 def test_assign_is_deterministic(td):
     dist, cab_to, cust_from = g.config1b()
     n, cost = cost_ref.calculate_cost_np(dist, cab_to, cust_from)
