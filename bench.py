@@ -836,6 +836,33 @@ def run_components(torch, np, g, eng, lib, _lib, dispatch, hbm_peak, flush_l2):
             del host, dcost
         if name == "assign_20k_5A_uniform":
             del cost
+    # K2 on the reference's own sizes: config 1 (python.py: 200 x 200, uniform and stand-derived with 10 dummy rows) and
+    # config 2 (2000 x 2000); CPU beside it: scipy linprog (HiGHS) on the reference's 2n x n^2 model (python.py's path;
+    # n = 200 only -- the dense model of solver.py:15-19 needs 128 GB at n = 2000) and scipy's LSA, one host core
+    from oracle import assign_ref, cost_ref
+    d1, cab1, cust1 = g.config1b()
+    _, c1b = cost_ref.calculate_cost_np(d1, cab1, cust1)
+    for name, Mnp, lp in (("assign_200_1A_uniform", g.config1a(), True), ("assign_200_1B_stand_padded", c1b, True),
+                          ("assign_2000_2_uniform", g.config2(), False), ("assign_2000_2_stand", g.config2_stand(), False)):
+        Md = torch.from_numpy(np.ascontiguousarray(Mnp, dtype=np.int32)).cuda()
+        res = {}
+
+        def solve_small():
+            col, obj, _, _ = eng.assign(Md)
+            res["obj"] = obj
+        ms, _ = timed(solve_small, reps=10, warm=3)
+        t0 = time.perf_counter()
+        ref_obj, _ = assign_ref.solve_scipy(Mnp)
+        lsa_s = time.perf_counter() - t0
+        assert int(res["obj"].item()) == ref_obj, name
+        out[name] = {"time_to_optimal_s": statistics.median(ms) * 1e-3, "objective": ref_obj, "n": int(Mnp.shape[0]),
+                     "cpu_scipy_lsa_s": lsa_s, "cpu_cores": 1}
+        if lp:
+            t0 = time.perf_counter()
+            lp_obj = assign_ref.lp_relaxation(Mnp)[0]
+            out[name]["cpu_scipy_linprog_highs_s"] = time.perf_counter() - t0
+            out[name]["lp_relaxation_rel_err"] = abs(lp_obj - ref_obj) / max(abs(ref_obj), 1)
+        del Md
     # K3: LCM on 2000 x 2000 (config 2), heuristic.py variant
     c2 = torch.from_numpy(g.config2()).cuda()
     ms, r = timed(lambda: eng.lcm(c2, 100), reps=10, warm=3)
@@ -843,7 +870,12 @@ def run_components(torch, np, g, eng, lib, _lib, dispatch, hbm_peak, flush_l2):
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "lcm.json")))["config2_heuristic"]
     assert hv["total"] == golden["total"], "LCM total differs from the golden trace"
     med = statistics.median(ms)
-    out["lcm_2000"] = {"ms": med, "lcm_per_s": 1e3 / med, "total": hv["total"],
+    t0 = time.perf_counter()
+    from oracle import lcm_ref
+    cpu_tot = lcm_ref.lcm_c(g.config2(), 100)["total"]          # literal array algorithm (C twin of heuristic.py:24-33), one core
+    lcm_cpu_s = time.perf_counter() - t0
+    assert cpu_tot == hv["total"]
+    out["lcm_2000"] = {"ms": med, "lcm_per_s": 1e3 / med, "total": hv["total"], "cpu_literal_c_s": lcm_cpu_s, "cpu_cores": 1,
                        "roofline": {"bound": "hbm", "achieved": 4 * 2000 * 2000 / (med * 1e-3) / 1e9, "peak": hbm_peak,
                                     "unit": "GB/s", "frac": 4 * 2000 * 2000 / (med * 1e-3) / 1e9 / hbm_peak,
                                     "bytes_model": "4 n^2 (each cost read once); L2-resident and sync-latency bound"}}
