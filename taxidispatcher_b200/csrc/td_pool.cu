@@ -68,7 +68,10 @@ struct PoolRec {                  // 16 bytes
 constexpr int kMaxSlots = 64;     // logical shards handled by one call
 constexpr int kBuckets = 256;     // cost histogram resolution (last bucket: cost >= 255)
 constexpr int kMaxBands = 8;      // cost bands of the selection; band sizes grow 4x from kBand0
-constexpr unsigned kBand0 = 4096;
+// Measured on config 3 (B200, 8 shards / 1 shard per call, select in us): 4096 x4: 917 / 294, 32768 x3: 720 / 259,
+// 65536 x4: 706 / 252, 131072 x4: 791 / 301, 262144 x4: 805 / 311 -- a first band of 65 536 records keeps the number of
+// grid-wide phases down without letting the last band (most of the records, few of them live) grow
+constexpr unsigned kBand0 = 65536;
 
 struct PoolCtrl {
     // ---- persistent over the passes of one call ----
@@ -718,6 +721,7 @@ struct SelArgs {
     unsigned int step_inv;                      // ceil(2^32 / step): p0 / step == umulhi(p0, step_inv) for p0, step <= 2^14 (p0 * step < 2^32)
     int first_pass;                             // 1: every customer starts free; 0: keep alive[] from the earlier windows
     int cost_hi;                                // records with cost >= cost_hi were counted in hist but not materialised
+    unsigned int band0, band_growth;            // records of the first cost band, growth factor of the band sizes
 };
 
 __device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
@@ -777,7 +781,7 @@ pool_select_kernel(SelArgs a) {
         for (int bkt = threadIdx.x; bkt < kBuckets; bkt += blockDim.x) s_hist[bkt] = bkt < a.cost_hi ? unsigned(ctrl->hist[sl][bkt]) : 0u;   // materialised records: < 2^32
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long cum = 0, target = kBand0;
+            unsigned long long cum = 0, target = a.band0;
             unsigned in_band = 0;
             int band = 0;
             for (int bkt = 0; bkt < kBuckets; ++bkt) {
@@ -787,7 +791,7 @@ pool_select_kernel(SelArgs a) {
                     ctrl->band_hi[sl][band] = bkt + 1;
                     ctrl->band_cnt[sl][band] = in_band;
                     atomicAdd(&ctrl->band_off[band + 1], in_band);   // sizes first, prefix below
-                    ++band; in_band = 0; target = cum * 4;
+                    ++band; in_band = 0; target = cum * (unsigned long long)a.band_growth;
                 }
             }
             ctrl->band_hi[sl][band] = INT_MAX;
@@ -1571,6 +1575,9 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
         sa.step_inv = step > 1 ? unsigned(((1ull << 32) + unsigned(step) - 1) / unsigned(step)) : 0u;
         sa.first_pass = first ? 1 : 0;
         sa.cost_hi = window_hi;
+        sa.band0 = kBand0; sa.band_growth = 4;
+        if (const char *e = getenv("TD_SEL_BAND0")) sa.band0 = unsigned(atoi(e));
+        if (const char *e = getenv("TD_SEL_GROWTH")) sa.band_growth = unsigned(atoi(e));
         void *sargs[] = {(void *)&sa};
         {
             ProfScope prof(TD_PROF_POOL_SELECT, st);
@@ -1737,6 +1744,7 @@ extern "C" int td_pool_pairs(const int32_t *from, const int32_t *to, int n, cons
     sa.best_hi[0] = w.best_hi[0]; sa.best_hi[1] = w.best_hi[1]; sa.best_lo[0] = w.best_lo[0]; sa.best_lo[1] = w.best_lo[1];
     sa.alive = w.alive; sa.kept = w.kept; sa.n = n; sa.K = 2;
     sa.n_slots = 1; sa.step = n + 1; sa.shard_begin = 0; sa.keep_cap = n / 2 + 1; sa.first_pass = 1; sa.cost_hi = INT_MAX;
+    sa.band0 = kBand0; sa.band_growth = 4;
     sa.step_inv = unsigned(((1ull << 32) + unsigned(n + 1) - 1) / unsigned(n + 1));   // n >= 2 here
     int per_sm = 0;
     TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_select_kernel, kSelThreads, 0));
