@@ -722,6 +722,7 @@ struct SelArgs {
     int first_pass;                             // 1: every customer starts free; 0: keep alive[] from the earlier windows
     int cost_hi;                                // records with cost >= cost_hi were counted in hist but not materialised
     unsigned int band0, band_growth;            // records of the first cost band, growth factor of the band sizes
+    unsigned int frag_cap;                      // records per CTA fragment of act[] (see the filter step)
 };
 
 __device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
@@ -893,23 +894,33 @@ pool_select_kernel(SelArgs a) {
         const unsigned b0 = ctrl->band_off[band], b1 = ctrl->band_off[band + 1];
         if (b0 == b1) continue;   // uniform: nothing in this band
         // ---- filter: live records of the band -> active list, first-level minima on the fly -------------------
+        // The active list is FRAGMENTED over the CTAs: a CTA appends the live records of its chunks to its own fragment
+        // (shared-memory cursor: no block barrier and no global atomic with a return value inside the loops) and every
+        // later pass of the band works on that fragment.  Only the totals (termination test), alive[] and the
+        // per-customer minima are shared through global memory.
+        __shared__ unsigned s_cnt;               // records in this CTA's fragment of the list being written
+        const size_t frag = size_t(blockIdx.x) * a.frag_cap;
+        unsigned my_cnt = 0;
         {
             constexpr int kFiltPer = 4;
-            __shared__ unsigned s_fcnt, s_fbase;
             const PoolRec *src = a.list[1];
-            PoolRec *act = a.act[0];
-            const unsigned chunk = blockDim.x * kFiltPer;
+            PoolRec *act = a.act[0] + frag;
+            // records per thread and chunk: fewer for a small band, so that its live records (and with them the work of
+            // the rounds, which stay on the fragments) spread over more CTAs
+            const unsigned want = (b1 - b0 + nthreads - 1) / nthreads;
+            const int per = want >= unsigned(kFiltPer) ? kFiltPer : (want < 1u ? 1 : int(want));
+            const unsigned chunk = blockDim.x * per;
+            __syncthreads();
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
             for (unsigned base = b0 + blockIdx.x * chunk; base < b1; base += gridDim.x * chunk) {
-                if (threadIdx.x == 0) s_fcnt = 0;
-                __syncthreads();
                 PoolRec r[kFiltPer];
                 bool live[kFiltPer];
                 int p[kFiltPer][4];
-                unsigned lrank[kFiltPer];
 #pragma unroll
                 for (int u = 0; u < kFiltPer; ++u) {
                     const unsigned i = base + u * blockDim.x + threadIdx.x;
-                    live[u] = i < b1;
+                    live[u] = u < per && i < b1;
                     if (live[u]) r[u] = src[i];
                 }
 #pragma unroll
@@ -923,25 +934,23 @@ pool_select_kernel(SelArgs a) {
                     live[u] = ok;
                 }
 #pragma unroll
-                for (int u = 0; u < kFiltPer; ++u) {   // warp-aggregated shared-memory counter
+                for (int u = 0; u < kFiltPer; ++u) {   // warp-aggregated shared-memory cursor
                     const unsigned ball = __ballot_sync(0xffffffffu, live[u]);
+                    if (ball == 0) continue;
                     unsigned wbase = 0;
-                    if (lane == 0 && ball) wbase = atomicAdd(&s_fcnt, __popc(ball));
+                    if (lane == 0) wbase = atomicAdd(&s_cnt, __popc(ball));
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    lrank[u] = wbase + __popc(ball & ((1u << lane) - 1));
-                }
-                __syncthreads();
-                if (threadIdx.x == 0 && s_fcnt) s_fbase = atomicAdd(&ctrl->act_cnt[band][0], s_fcnt);
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < kFiltPer; ++u) {
-                    if (!live[u]) continue;
-                    act[s_fbase + lrank[u]] = r[u];
-                    const unsigned long long hi = single_key ? rec_key1(r[u], cb) : rec_hi(r[u]);
-                    for (int q = 0; q < K; ++q)
-                        if (hi < a.best_hi[par][p[u][q]]) atomicMin(&a.best_hi[par][p[u][q]], hi);
+                    if (live[u]) {
+                        act[wbase + __popc(ball & ((1u << lane) - 1))] = r[u];
+                        const unsigned long long hi = single_key ? rec_key1(r[u], cb) : rec_hi(r[u]);
+                        for (int q = 0; q < K; ++q)   // the test spares most of the atomics: same-address atomics serialise in L2
+                            if (hi < a.best_hi[par][p[u][q]]) atomicMin(&a.best_hi[par][p[u][q]], hi);
+                    }
                 }
             }
+            __syncthreads();
+            my_cnt = s_cnt;
+            if (threadIdx.x == 0 && my_cnt) atomicAdd(&ctrl->act_cnt[band][0], my_cnt);
         }
         grid.sync();
         stamp();
@@ -949,18 +958,17 @@ pool_select_kernel(SelArgs a) {
         unsigned al = 0;
         for (unsigned r = 0;; ++r) {
             if (r > 0) {   // pass A: drop the plans killed by the previous round, compact, first-level minima
-                __shared__ unsigned s_acnt, s_abase;
-                const unsigned acnt = ctrl->act_cnt[band][al];
-                const PoolRec *src = a.act[al];
-                PoolRec *dst = a.act[al ^ 1];
-                for (unsigned base = blockIdx.x * blockDim.x; base < acnt; base += nthreads) {
-                    if (threadIdx.x == 0) s_acnt = 0;
-                    __syncthreads();
+                const PoolRec *src = a.act[al] + frag;
+                PoolRec *dst = a.act[al ^ 1] + frag;
+                __syncthreads();
+                if (threadIdx.x == 0) s_cnt = 0;
+                __syncthreads();
+                for (unsigned base = 0; base < my_cnt; base += blockDim.x) {
                     const unsigned i = base + threadIdx.x;
                     bool live = false;
                     PoolRec rec;
                     int p[4], perm;
-                    if (i < acnt) {
+                    if (i < my_cnt) {
                         rec = src[i];
                         split_rank(rec.rank, p, perm);
                         live = true;
@@ -968,29 +976,29 @@ pool_select_kernel(SelArgs a) {
                         for (int q = 0; q < K; ++q) { p[q] += so; live = live && a.alive[p[q]]; }
                     }
                     const unsigned ball = __ballot_sync(0xffffffffu, live);
+                    if (ball == 0) continue;
                     unsigned wbase = 0;
-                    if (lane == 0 && ball) wbase = atomicAdd(&s_acnt, __popc(ball));
+                    if (lane == 0) wbase = atomicAdd(&s_cnt, __popc(ball));
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    const unsigned lrank = wbase + __popc(ball & ((1u << lane) - 1));
-                    __syncthreads();
-                    if (threadIdx.x == 0 && s_acnt) s_abase = atomicAdd(&ctrl->act_cnt[band][al ^ 1], s_acnt);
-                    __syncthreads();
                     if (live) {
-                        dst[s_abase + lrank] = rec;
+                        dst[wbase + __popc(ball & ((1u << lane) - 1))] = rec;
                         const unsigned long long hi = single_key ? rec_key1(rec, cb) : rec_hi(rec);
                         for (int q = 0; q < K; ++q)
                             if (hi < a.best_hi[par][p[q]]) atomicMin(&a.best_hi[par][p[q]], hi);
                     }
                 }
+                __syncthreads();
+                my_cnt = s_cnt;
+                if (threadIdx.x == 0 && my_cnt) atomicAdd(&ctrl->act_cnt[band][al ^ 1], my_cnt);
                 grid.sync();
                 al ^= 1;
             }
             const unsigned n_act = ctrl->act_cnt[band][al];
             if (n_act == 0) break;
-            const PoolRec *cur = a.act[al];
+            const PoolRec *cur = a.act[al] + frag;
             // pass B: second-level minimum among the plans that tie on the first level (two-level keys only)
             if (!single_key)
-            for (unsigned i = tid; i < n_act; i += nthreads) {
+            for (unsigned i = threadIdx.x; i < my_cnt; i += blockDim.x) {
                 const PoolRec rec = cur[i];
                 int p[4], perm;
                 split_rank(rec.rank, p, perm);
@@ -1003,7 +1011,7 @@ pool_select_kernel(SelArgs a) {
             if (tid == 0) ctrl->act_cnt[band][al ^ 1] = 0;   // target of the next round's pass A
             if (!single_key) grid.sync();
             // pass C: keep the plans that hold the minimum at every one of their customers
-            for (unsigned i = tid; i < n_act; i += nthreads) {
+            for (unsigned i = threadIdx.x; i < my_cnt; i += blockDim.x) {
                 const PoolRec rec = cur[i];
                 int p[4], perm;
                 split_rank(rec.rank, p, perm);
@@ -1376,6 +1384,12 @@ struct PoolWorkspace {
     unsigned long long *best_hi[2]; unsigned int *best_lo[2]; uint8_t *alive; PoolCtrl *ctrl; size_t bytes;
 };
 
+// act[] is cut into one fragment per CTA of pool_select (at most kSelMaxGrid CTAs): a CTA filters whole chunks of
+// kSelThreads * 4 records, so its fragment holds its share of the list plus one chunk
+constexpr int kSelMaxGrid = 640;
+constexpr size_t kActSlack = size_t(kSelMaxGrid) * (kSelThreads * 4 + 1);
+static unsigned sel_frag_cap(int64_t max_records, int grid) { return unsigned(max_records / grid) + kSelThreads * 4 + 1; }
+
 static PoolWorkspace carve_pool(void *ws, int n, int S, int n_slots, int64_t max_records) {
     Carver c(ws);
     PoolWorkspace w;
@@ -1392,8 +1406,8 @@ static PoolWorkspace carve_pool(void *ws, int n, int S, int n_slots, int64_t max
     w.item_off = c.take<unsigned int>(nn + 2);
     w.recs[0] = c.take<PoolRec>(size_t(max_records));
     w.recs[1] = c.take<PoolRec>(size_t(max_records));
-    w.act[0] = c.take<PoolRec>(size_t(max_records));
-    w.act[1] = c.take<PoolRec>(size_t(max_records));
+    w.act[0] = c.take<PoolRec>(size_t(max_records) + kActSlack);   // fragmented over the CTAs of pool_select
+    w.act[1] = c.take<PoolRec>(size_t(max_records) + kActSlack);
     w.kept = c.take<PoolRec>(size_t(n_slots > 0 ? n_slots : 1) * (nn / 2 + 1));
     w.best_hi[0] = c.take<unsigned long long>(ns);
     w.best_hi[1] = c.take<unsigned long long>(ns);
@@ -1547,7 +1561,8 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
     if (sel_per_sm < 1) return TD_ERR_CUDA;
     sel_per_sm = sel_per_sm > 4 ? 4 : sel_per_sm;
     if (const char *e = getenv("TD_SEL_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= sel_per_sm) sel_per_sm = v; }
-    if (sms * sel_per_sm < shard_count) return TD_ERR_INVALID;
+    while (sel_per_sm > 1 && sms * sel_per_sm > kSelMaxGrid) --sel_per_sm;
+    if (sms * sel_per_sm < shard_count || sms * sel_per_sm > kSelMaxGrid) return TD_ERR_INVALID;
 
     // the per-pass part of the control block (everything after pass_begin_marker)
     const size_t pass_off = offsetof(PoolCtrl, pass_begin_marker);
@@ -1575,6 +1590,7 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
         sa.step_inv = step > 1 ? unsigned(((1ull << 32) + unsigned(step) - 1) / unsigned(step)) : 0u;
         sa.first_pass = first ? 1 : 0;
         sa.cost_hi = window_hi;
+        sa.frag_cap = sel_frag_cap(rec_cap64, sms * sel_per_sm);
         sa.band0 = kBand0; sa.band_growth = 4;
         if (const char *e = getenv("TD_SEL_BAND0")) sa.band0 = unsigned(atoi(e));
         if (const char *e = getenv("TD_SEL_GROWTH")) sa.band_growth = unsigned(atoi(e));
@@ -1750,6 +1766,9 @@ extern "C" int td_pool_pairs(const int32_t *from, const int32_t *to, int n, cons
     TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pool_select_kernel, kSelThreads, 0));
     if (per_sm < 1) return TD_ERR_CUDA;
     per_sm = per_sm > 4 ? 4 : per_sm;
+    while (per_sm > 1 && sms * per_sm > kSelMaxGrid) --per_sm;
+    if (sms * per_sm > kSelMaxGrid) return TD_ERR_INVALID;
+    sa.frag_cap = sel_frag_cap(recs, sms * per_sm);
     void *sargs[] = {(void *)&sa};
     {
         ProfScope prof(TD_PROF_POOL_SELECT, st);
