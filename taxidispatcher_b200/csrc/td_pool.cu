@@ -221,7 +221,7 @@ pool_check_table_kernel(const int32_t *__restrict__ dist, long long cells, PoolC
 // leaves, one at a time).  pool_enum<4> uses the bound to skip those leaves; they are still COUNTED (pool_n.c:103).
 // On metric tables (|i-j|, pool_n.c:179-185) D* == D.  A table with a negative entry switches the bound off.
 constexpr int kPfMaxStands = 128;
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict__ dclose, int sh, PoolCtrl *ctrl) {
     extern __shared__ int32_t s_d[];
     const int cells = S * S;
@@ -234,12 +234,13 @@ pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict
         s_d[i] = v;
     }
     neg = __syncthreads_or(neg);
-    // 32 x 32 thread tile over the table (no index division in the k loop); row k and column k do not change in step k
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // 16 x 16 thread tile over the table (8 warps: a cheap block barrier per step, no index division in the k loop);
+    // row k and column k do not change in step k
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     for (int k = 0; k < S; ++k) {
-        for (int r = ty; r < S; r += 32) {
+        for (int r = ty; r < S; r += 16) {
             const int rk = s_d[r * S + k];
-            for (int c = tx; c < S; c += 32) {
+            for (int c = tx; c < S; c += 16) {
                 const int via = rk + s_d[k * S + c];
                 if (via < s_d[r * S + c]) s_d[r * S + c] = via;
             }
@@ -526,6 +527,8 @@ pool_enum_kernel(EnumArgs a) {
     };
 
     for (;;) {
+        // (requesting the next item ahead of time to hide the atomic's latency was measured and dropped: a warp then
+        // sits on an item while others idle at the tail -- 8 shards 0.60 -> 0.62 ms, one shard 0.13 -> 0.17 ms)
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(&a.ctrl->item_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
@@ -1576,7 +1579,7 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
     if (closure) {
         const size_t cl_smem = size_t(n_stands) * n_stands * 4;
         TD_CUDA_TRY(cudaFuncSetAttribute(pool_closure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(64 * 1024)));
-        pool_closure_kernel<<<1, 1024, cl_smem, st>>>(dist, n_stands, w.dclose, sh, w.ctrl);
+        pool_closure_kernel<<<1, 256, cl_smem, st>>>(dist, n_stands, w.dclose, sh, w.ctrl);
         TD_LAUNCH_CHECK();
     }
 
