@@ -50,7 +50,7 @@ namespace td {
 
 constexpr int kTbl = 64;          // budget table entries per stand
 constexpr int kEnumThreads = 256;
-constexpr int kEnumThreadsWide = 768;   // one CTA per SM (big staged tables): 24 warps instead of 8
+constexpr int kEnumThreadsWide = 1024;  // one CTA per SM (big staged tables): 32 warps instead of 8
 constexpr int kIoffSmem = 2048;          // leaders whose item offsets are staged in shared memory
 constexpr size_t kEnumIoffBytes = (size_t(kIoffSmem) + 4) * 4;
 constexpr size_t kEnumWarpBytes = 256 * 4 + 3 * 32 * 16 + 64 * 8;   // histogram + staging A, B, C + tuple queue
