@@ -783,7 +783,7 @@ __device__ __forceinline__ unsigned long long rec_key1(const PoolRec &r, int cb)
 //                   different shards never interact because their state is indexed by shard).
 // Each record is read ~3 times in total; the rounds touch only the live in-band records
 // (config 3: ~0.3 M record visits per shard instead of ~7.5 M x 3 passes on the unbanded list).
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, 2)   // 64 registers: two CTAs per SM keep the streaming passes fed
 pool_select_kernel(SelArgs a) {
     cg::grid_group grid = cg::this_grid();
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -957,9 +957,10 @@ pool_select_kernel(SelArgs a) {
                     int perm;
                     split_rank(r[u].rank, p[u], perm);
                     const int so = slot_of(p[u][0]) * n;
-                    bool ok = true;
-                    for (int q = 0; q < K; ++q) { p[u][q] += so; ok = ok && a.alive[p[u][q]]; }
-                    live[u] = ok;
+                    uint8_t fl[4];                       // the four flags are loaded together (no short-circuit chain)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { p[u][q] += so; fl[q] = q < K ? a.alive[p[u][q]] : uint8_t(1); }
+                    live[u] = fl[0] && fl[1] && fl[2] && fl[3];
                 }
 #pragma unroll
                 for (int u = 0; u < kFiltPer; ++u) {   // warp-aggregated shared-memory cursor
@@ -971,8 +972,16 @@ pool_select_kernel(SelArgs a) {
                     if (live[u]) {
                         act[wbase + __popc(ball & ((1u << lane) - 1))] = r[u];
                         const unsigned long long hi = single_key ? rec_key1(r[u], cb) : rec_hi(r[u]);
-                        for (int q = 0; q < K; ++q)   // the test spares most of the atomics: same-address atomics serialise in L2
-                            if (hi < a.best_hi[par][p[u][q]]) atomicMin(&a.best_hi[par][p[u][q]], hi);
+                        // the test spares most of the atomics (same-address atomics serialise in L2); the four current minima
+                        // are loaded TOGETHER before the first atomic -- behind an atomic the compiler may not hoist the next
+                        // load, which made this four dependent L2 round trips per live record.  A stale (larger) value only
+                        // costs a redundant atomic.
+                        unsigned long long cur4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cur4[q] = q < K ? a.best_hi[par][p[u][q]] : 0ull;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < K && hi < cur4[q]) atomicMin(&a.best_hi[par][p[u][q]], hi);
                     }
                 }
             }
@@ -999,9 +1008,11 @@ pool_select_kernel(SelArgs a) {
                     if (i < my_cnt) {
                         rec = src[i];
                         split_rank(rec.rank, p, perm);
-                        live = true;
                         const int so = slot_of(p[0]) * n;
-                        for (int q = 0; q < K; ++q) { p[q] += so; live = live && a.alive[p[q]]; }
+                        uint8_t fl[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { p[q] += so; fl[q] = q < K ? a.alive[p[q]] : uint8_t(1); }
+                        live = fl[0] && fl[1] && fl[2] && fl[3];
                     }
                     const unsigned ball = __ballot_sync(0xffffffffu, live);
                     if (ball == 0) continue;
@@ -1011,8 +1022,12 @@ pool_select_kernel(SelArgs a) {
                     if (live) {
                         dst[wbase + __popc(ball & ((1u << lane) - 1))] = rec;
                         const unsigned long long hi = single_key ? rec_key1(rec, cb) : rec_hi(rec);
-                        for (int q = 0; q < K; ++q)
-                            if (hi < a.best_hi[par][p[q]]) atomicMin(&a.best_hi[par][p[q]], hi);
+                        unsigned long long cur4[4];          // loaded together, see the filter
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cur4[q] = q < K ? a.best_hi[par][p[q]] : 0ull;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < K && hi < cur4[q]) atomicMin(&a.best_hi[par][p[q]], hi);
                     }
                 }
                 __syncthreads();
@@ -1047,9 +1062,15 @@ pool_select_kernel(SelArgs a) {
                 const int so = slot * n;
                 const unsigned long long hi = single_key ? rec_key1(rec, cb) : rec_hi(rec);
                 const unsigned lo = unsigned(rec.rank);
-                bool dom = true;
-                if (single_key) { for (int q = 0; q < K; ++q) dom = dom && a.best_hi[par][so + p[q]] == hi; }
-                else for (int q = 0; q < K; ++q) dom = dom && a.best_hi[par][so + p[q]] == hi && a.best_lo[par][so + p[q]] == lo;
+                unsigned long long bh[4];
+                unsigned bl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {            // loaded together, then compared
+                    bh[q] = q < K ? a.best_hi[par][so + p[q]] : hi;
+                    bl[q] = (q < K && !single_key) ? a.best_lo[par][so + p[q]] : lo;
+                }
+                const bool dom = bh[0] == hi && bh[1] == hi && bh[2] == hi && bh[3] == hi &&
+                                 bl[0] == lo && bl[1] == lo && bl[2] == lo && bl[3] == lo;
                 if (dom) {
                     const unsigned pos = atomicAdd(&ctrl->n_kept[slot], 1u);
                     a.kept[size_t(slot) * a.keep_cap + pos] = rec;
