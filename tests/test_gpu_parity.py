@@ -226,6 +226,38 @@ def test_pool_random_tables_vs_oracle(td, k):
         assert np.array_equal(plans, oplans)
 
 
+def test_pool_k4_pruning_bounds_fuzz(td):
+    """the exact pruning bounds of the K = 4 enumeration (shortest-path closure, last-dropped passenger) on tables that
+    break the triangle inequality in different ways: sparse zeros, one-way shortcuts, constant rows, from == to trips,
+    waits at and around the feasibility edge.  Counters and plans must equal the oracle case by case."""
+    rng = np.random.default_rng(20261018)
+    for case in range(36):
+        S = int(rng.integers(3, 30))
+        n = int(rng.integers(8, 56))
+        kind = case % 4
+        if kind == 0:                                    # metric line with random one-way shortcuts
+            dist = np.abs(np.arange(S)[:, None] - np.arange(S)[None, :]).astype(np.int32)
+            for _ in range(S):
+                dist[rng.integers(0, S), rng.integers(0, S)] = rng.integers(0, 3)
+        elif kind == 1:                                  # mostly zeros
+            dist = (rng.integers(0, 10, (S, S)) * (rng.random((S, S)) < 0.3)).astype(np.int32)
+        elif kind == 2:                                  # wide range, asymmetric
+            dist = rng.integers(0, 200, (S, S)).astype(np.int32)
+        else:                                            # constant rows (every leg out of a stand costs the same)
+            dist = np.repeat(rng.integers(1, 12, (S, 1)), S, axis=1).astype(np.int32)
+        np.fill_diagonal(dist, 0)
+        fr = rng.integers(0, S, n)
+        to = np.where(rng.random(n) < 0.1, fr, rng.integers(0, S, n))     # some trips end where they start
+        scale = max(1, int(dist.max()))
+        dem = np.stack([np.arange(n), fr, to, rng.integers(0, 3 * scale + 1, n), rng.integers(0, 150, n)], axis=1).astype(np.int32)
+        n_shards = int(rng.integers(1, 9))
+        shard = int(rng.integers(0, n_shards))
+        plans, st = td.find_pool(dem, dist, 4, shard, n_shards)
+        oplans, ost = pool_ref.find(dem, dist, 4, shard, n_shards)
+        assert {q: st[q] for q in ost} == ost, (case, kind, S, n)
+        assert np.array_equal(plans, oplans), (case, kind, S, n)
+
+
 @pytest.mark.parametrize("k", [2, 3, 4])
 def test_pool_large_costs_take_the_two_level_keys(td, k):
     """plan costs >= 255 fall into the open-ended histogram bucket: the selection cannot pack (cost, rank) into one
