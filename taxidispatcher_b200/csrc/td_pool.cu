@@ -753,6 +753,15 @@ struct SelArgs {
     unsigned int frag_cap;                      // records per CTA fragment of act[] (see the filter step)
 };
 
+__device__ __forceinline__ unsigned long long sel_warp_min(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
 __device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
     return ((unsigned long long)(unsigned)r.cost << 32) | (r.rank >> 32);
 }
@@ -969,18 +978,26 @@ pool_select_kernel(SelArgs a) {
                     unsigned wbase = 0;
                     if (lane == 0) wbase = atomicAdd(&s_cnt, __popc(ball));
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    // The live records of a warp mostly share their leader (emission order survives the partition in runs):
+                    // one atomic on the leader's cell per warp instead of one per record -- same-address atomics serialise
+                    // in L2 and the leader cells are the hottest (a shard has ~n/8 leaders for all its records).
+                    const unsigned long long hi = live[u] ? (single_key ? rec_key1(r[u], cb) : rec_hi(r[u])) : ~0ull;
+                    const int cell0 = live[u] ? p[u][0] : -1;
+                    const int lead = __ffs(ball) - 1;
+                    const int lead_cell = __shfl_sync(0xffffffffu, cell0, lead);   // outside the ||: every lane must execute it
+                    const bool shared0 = __all_sync(0xffffffffu, !live[u] || cell0 == lead_cell);
+                    const unsigned long long wmin = shared0 ? sel_warp_min(hi) : hi;
                     if (live[u]) {
                         act[wbase + __popc(ball & ((1u << lane) - 1))] = r[u];
-                        const unsigned long long hi = single_key ? rec_key1(r[u], cb) : rec_hi(r[u]);
-                        // the test spares most of the atomics (same-address atomics serialise in L2); the four current minima
-                        // are loaded TOGETHER before the first atomic -- behind an atomic the compiler may not hoist the next
-                        // load, which made this four dependent L2 round trips per live record.  A stale (larger) value only
-                        // costs a redundant atomic.
+                        // the test spares most of the atomics; the four current minima are loaded TOGETHER before the first
+                        // atomic -- behind an atomic the compiler may not hoist the next load, which made this four dependent
+                        // L2 round trips per live record.  A stale (larger) value only costs a redundant atomic.
                         unsigned long long cur4[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) cur4[q] = q < K ? a.best_hi[par][p[u][q]] : 0ull;
+                        if (!shared0 || int(lane) == lead) { if (wmin < cur4[0]) atomicMin(&a.best_hi[par][p[u][0]], wmin); }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
+                        for (int q = 1; q < 4; ++q)
                             if (q < K && hi < cur4[q]) atomicMin(&a.best_hi[par][p[u][q]], hi);
                     }
                 }
@@ -1019,14 +1036,20 @@ pool_select_kernel(SelArgs a) {
                     unsigned wbase = 0;
                     if (lane == 0) wbase = atomicAdd(&s_cnt, __popc(ball));
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    const unsigned long long hi = live ? (single_key ? rec_key1(rec, cb) : rec_hi(rec)) : ~0ull;
+                    const int cell0 = live ? p[0] : -1;       // one atomic per warp on a shared leader cell, see the filter
+                    const int lead = __ffs(ball) - 1;
+                    const int lead_cell = __shfl_sync(0xffffffffu, cell0, lead);
+                    const bool shared0 = __all_sync(0xffffffffu, !live || cell0 == lead_cell);
+                    const unsigned long long wmin = shared0 ? sel_warp_min(hi) : hi;
                     if (live) {
                         dst[wbase + __popc(ball & ((1u << lane) - 1))] = rec;
-                        const unsigned long long hi = single_key ? rec_key1(rec, cb) : rec_hi(rec);
                         unsigned long long cur4[4];          // loaded together, see the filter
 #pragma unroll
                         for (int q = 0; q < 4; ++q) cur4[q] = q < K ? a.best_hi[par][p[q]] : 0ull;
+                        if (!shared0 || int(lane) == lead) { if (wmin < cur4[0]) atomicMin(&a.best_hi[par][p[0]], wmin); }
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
+                        for (int q = 1; q < 4; ++q)
                             if (q < K && hi < cur4[q]) atomicMin(&a.best_hi[par][p[q]], hi);
                     }
                 }
