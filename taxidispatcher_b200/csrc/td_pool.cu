@@ -753,6 +753,11 @@ struct SelArgs {
     unsigned int frag_cap;                      // records per CTA fragment of act[] (see the filter step)
 };
 
+// Minimum of `key` over the run of consecutive lanes that hold the same cell (any lanes with an equal cell may be
+// folded in: every one of them is a valid contribution to that cell).  Returns true on the first lane of a run -- the one
+// that issues the atomic for it.  Emission order survives the partition and the compaction in runs, so consecutive
+// records share the leader, mostly the second pickup and often the third: one atomic per run instead of one per record
+// (same-address atomics serialise in L2).  Every lane of the warp must call it.
 __device__ __forceinline__ unsigned long long sel_warp_min(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -760,6 +765,22 @@ __device__ __forceinline__ unsigned long long sel_warp_min(unsigned long long v)
         v = w < v ? w : v;
     }
     return v;
+}
+
+constexpr int kRunMinLive = 12;   // live records in a warp's batch from which the run minima are taken
+__device__ __forceinline__ bool sel_run_min(int cell, unsigned long long &key, bool live, unsigned ball, unsigned lane) {
+    // dead lanes (key = ~0) take the cell of the nearest live lane below them, so that they do not cut a run in two
+    const unsigned below = ball & ((1u << lane) - 1);
+    const int filled = __shfl_sync(0xffffffffu, cell, below ? 31 - __clz(below) : int(lane));
+    if (!live) cell = below ? filled : -1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int oc = __shfl_down_sync(0xffffffffu, cell, o);
+        const unsigned long long ok = __shfl_down_sync(0xffffffffu, key, o);
+        if (lane + o < 32 && oc == cell && ok < key) key = ok;
+    }
+    const int pc = __shfl_up_sync(0xffffffffu, cell, 1);
+    return lane == 0 || pc != cell;
 }
 
 __device__ __forceinline__ unsigned long long rec_hi(const PoolRec &r) {
@@ -978,15 +999,25 @@ pool_select_kernel(SelArgs a) {
                     unsigned wbase = 0;
                     if (lane == 0) wbase = atomicAdd(&s_cnt, __popc(ball));
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    // The live records of a warp mostly share their leader (emission order survives the partition in runs):
-                    // one atomic on the leader's cell per warp instead of one per record -- same-address atomics serialise
-                    // in L2 and the leader cells are the hottest (a shard has ~n/8 leaders for all its records).
                     const unsigned long long hi = live[u] ? (single_key ? rec_key1(r[u], cb) : rec_hi(r[u])) : ~0ull;
-                    const int cell0 = live[u] ? p[u][0] : -1;
-                    const int lead = __ffs(ball) - 1;
-                    const int lead_cell = __shfl_sync(0xffffffffu, cell0, lead);   // outside the ||: every lane must execute it
-                    const bool shared0 = __all_sync(0xffffffffu, !live[u] || cell0 == lead_cell);
-                    const unsigned long long wmin = shared0 ? sel_warp_min(hi) : hi;
+                    unsigned long long rmin[3];
+                    bool head[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { rmin[q] = hi; head[q] = q < K; }
+                    if (band == 0 && __popc(ball) >= kRunMinLive) {   // uniform.  First band, dense survivors: per-run minima
+                                                                      // (sel_run_min); the later bands' survivors are sparse
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+                            if (q < K) head[q] = sel_run_min(live[u] ? p[u][q] : -1, rmin[q], live[u], ball, lane);
+                    } else {                                 // sparse survivors: only the leader's cell is worth a reduction
+                        const int cell0 = live[u] ? p[u][0] : -1;
+                        const int lead = __ffs(ball) - 1;
+                        const int lead_cell = __shfl_sync(0xffffffffu, cell0, lead);
+                        if (__all_sync(0xffffffffu, !live[u] || cell0 == lead_cell)) {
+                            rmin[0] = sel_warp_min(hi);
+                            head[0] = int(lane) == lead;
+                        }
+                    }
                     if (live[u]) {
                         act[wbase + __popc(ball & ((1u << lane) - 1))] = r[u];
                         // the test spares most of the atomics; the four current minima are loaded TOGETHER before the first
@@ -995,10 +1026,10 @@ pool_select_kernel(SelArgs a) {
                         unsigned long long cur4[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) cur4[q] = q < K ? a.best_hi[par][p[u][q]] : 0ull;
-                        if (!shared0 || int(lane) == lead) { if (wmin < cur4[0]) atomicMin(&a.best_hi[par][p[u][0]], wmin); }
 #pragma unroll
-                        for (int q = 1; q < 4; ++q)
-                            if (q < K && hi < cur4[q]) atomicMin(&a.best_hi[par][p[u][q]], hi);
+                        for (int q = 0; q < 3; ++q)
+                            if (head[q] && rmin[q] < cur4[q]) atomicMin(&a.best_hi[par][p[u][q]], rmin[q]);
+                        if (3 < K && hi < cur4[3]) atomicMin(&a.best_hi[par][p[u][3]], hi);
                     }
                 }
             }
@@ -1037,20 +1068,23 @@ pool_select_kernel(SelArgs a) {
                     if (lane == 0) wbase = atomicAdd(&s_cnt, __popc(ball));
                     wbase = __shfl_sync(0xffffffffu, wbase, 0);
                     const unsigned long long hi = live ? (single_key ? rec_key1(rec, cb) : rec_hi(rec)) : ~0ull;
-                    const int cell0 = live ? p[0] : -1;       // one atomic per warp on a shared leader cell, see the filter
-                    const int lead = __ffs(ball) - 1;
-                    const int lead_cell = __shfl_sync(0xffffffffu, cell0, lead);
-                    const bool shared0 = __all_sync(0xffffffffu, !live || cell0 == lead_cell);
-                    const unsigned long long wmin = shared0 ? sel_warp_min(hi) : hi;
+                    unsigned long long rmin[3];
+                    bool head[3];
+#pragma unroll
+                    const bool dense = __popc(ball) >= kRunMinLive;
+                    for (int q = 0; q < 3; ++q) {           // see the filter
+                        rmin[q] = hi;
+                        head[q] = q < K && ((q > 0 && !dense) || sel_run_min(live ? p[q] : -1, rmin[q], live, ball, lane));
+                    }
                     if (live) {
                         dst[wbase + __popc(ball & ((1u << lane) - 1))] = rec;
                         unsigned long long cur4[4];          // loaded together, see the filter
 #pragma unroll
                         for (int q = 0; q < 4; ++q) cur4[q] = q < K ? a.best_hi[par][p[q]] : 0ull;
-                        if (!shared0 || int(lane) == lead) { if (wmin < cur4[0]) atomicMin(&a.best_hi[par][p[0]], wmin); }
 #pragma unroll
-                        for (int q = 1; q < 4; ++q)
-                            if (q < K && hi < cur4[q]) atomicMin(&a.best_hi[par][p[q]], hi);
+                        for (int q = 0; q < 3; ++q)
+                            if (head[q] && rmin[q] < cur4[q]) atomicMin(&a.best_hi[par][p[q]], rmin[q]);
+                        if (3 < K && hi < cur4[3]) atomicMin(&a.best_hi[par][p[3]], hi);
                     }
                 }
                 __syncthreads();
