@@ -221,9 +221,50 @@ pool_check_table_kernel(const int32_t *__restrict__ dist, long long cells, PoolC
 // leaves, one at a time).  pool_enum<4> uses the bound to skip those leaves; they are still COUNTED (pool_n.c:103).
 // On metric tables (|i-j|, pool_n.c:179-185) D* == D.  A table with a negative entry switches the bound off.
 constexpr int kPfMaxStands = 128;
+template <int T>
+__device__ __forceinline__ void closure_steps(int S, int32_t *s_d, int32_t *s_line) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    constexpr int kBig = 1 << 28;
+    int d[T][T];
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            d[a][b] = (r < S && c < S) ? s_d[r * S + c] : kBig;
+        }
+    for (int k = 0; k < S; ++k) {
+        int32_t *row = s_line + (k & 1) * 2 * kPfMaxStands, *col = row + kPfMaxStands;
+        const int ka = k >> 4, kt = k & 15;
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) {
+                if (a == ka && ty == kt && tx + 16 * b < S) row[tx + 16 * b] = d[a][b];
+                if (b == ka && tx == kt && ty + 16 * a < S) col[ty + 16 * a] = d[a][b];
+            }
+        __syncthreads();
+        int rk[T], kc[T];
+#pragma unroll
+        for (int a = 0; a < T; ++a) { rk[a] = ty + 16 * a < S ? col[ty + 16 * a] : kBig; kc[a] = tx + 16 * a < S ? row[tx + 16 * a] : kBig; }
+#pragma unroll
+        for (int a = 0; a < T; ++a)
+#pragma unroll
+            for (int b = 0; b < T; ++b) d[a][b] = min(d[a][b], rk[a] + kc[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int b = 0; b < T; ++b) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            if (r < S && c < S) s_d[r * S + c] = d[a][b];
+        }
+}
+
 __global__ void __launch_bounds__(256)
 pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict__ dclose, int sh, PoolCtrl *ctrl) {
     extern __shared__ int32_t s_d[];
+    __shared__ int32_t s_line[2][2][kPfMaxStands];
     const int cells = S * S;
     int neg = 0;
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
@@ -234,19 +275,12 @@ pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict
         s_d[i] = v;
     }
     neg = __syncthreads_or(neg);
-    // 16 x 16 thread tile over the table (8 warps: a cheap block barrier per step, no index division in the k loop);
-    // row k and column k do not change in step k
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    for (int k = 0; k < S; ++k) {
-        for (int r = ty; r < S; r += 16) {
-            const int rk = s_d[r * S + k];
-            for (int c = tx; c < S; c += 16) {
-                const int via = rk + s_d[k * S + c];
-                if (via < s_d[r * S + c]) s_d[r * S + c] = via;
-            }
-        }
-        __syncthreads();
-    }
+    // 16 x 16 thread tile over the table, every thread keeps its T x T cells in registers.  Row k and column k do not
+    // change in step k (d(k,k) = 0, entries >= 0), so their owners publish them after step k - 1 into a double-buffered
+    // line pair: one block barrier and 2T shared-memory loads per step instead of two loads and a store per cell.
+    if (S <= 64) closure_steps<4>(S, s_d, s_line[0][0]);
+    else closure_steps<8>(S, s_d, s_line[0][0]);
+    __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) dclose[i] = (s_d[i] > kDistLimit ? kDistLimit : s_d[i]) << sh;   // D* <= D <= limit on accepted tables
     if (threadIdx.x == 0) ctrl->closure_ok = neg ? 0u : 1u;
 }
@@ -1543,14 +1577,14 @@ static int launch_enum(EnumArgs a, int sms, bool closure, cudaStream_t st) {
     const size_t tables = (ds ? dist_b : 0) + (pf ? dist_b : 0) + (cs ? ((cust_b + 15) & ~size_t(15)) : 0);
     const int n_lead = a.stop - a.start;
     a.ioff_bytes = unsigned(((size_t(n_lead <= kIoffSmem ? n_lead : 0) + 1) * 4 + 15) & ~size_t(15));   // staged only when they fit
-#define TD_ENUM_LAUNCH(DS, CS, PF, THR)                                                                                  \
+#define TD_ENUM_LAUNCH(DS, CS, PF, THR, FORCE)                                                                           \
     do {                                                                                                                 \
         auto kern = pool_enum_kernel<K, DS, CS, PF, THR>;                                                                \
         const size_t smem = tables + a.ioff_bytes + size_t(THR / 32) * kEnumWarpBytes;                                   \
         TD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(224 * 1024)));           \
         TD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THR, smem));                            \
-        if (per_sm < 1) return TD_ERR_CUDA;                                                                              \
-        if (THR == kEnumThreads && per_sm == 1 && K == 4 && !getenv("TD_ENUM_NARROW")) break;   /* take the wide CTA */ \
+        if (per_sm < 1) break;                                          /* does not fit: the caller tries the next   */ \
+        if (!(FORCE) && THR == kEnumThreads && per_sm == 1 && K == 4 && !getenv("TD_ENUM_NARROW")) break;   /* wide CTA */ \
         kern<<<sms * (per_sm > 4 ? 4 : per_sm), THR, smem, st>>>(a);   /* resident CTAs only: a CTA that starts     */ \
         launched = true;                                                /* late finds the queue empty                */ \
     } while (0)
@@ -1558,8 +1592,9 @@ static int launch_enum(EnumArgs a, int sms, bool closure, cudaStream_t st) {
     do {                                                                                                                 \
         int per_sm = 0;                                                                                                  \
         bool launched = false;                                                                                           \
-        TD_ENUM_LAUNCH(DS, CS, PF, kEnumThreads);                                                                        \
-        if (!launched) TD_ENUM_LAUNCH(DS, CS, PF, (K == 4 ? kEnumThreadsWide : kEnumThreads));                           \
+        TD_ENUM_LAUNCH(DS, CS, PF, kEnumThreads, false);                                                                 \
+        if (!launched) TD_ENUM_LAUNCH(DS, CS, PF, (K == 4 ? kEnumThreadsWide : kEnumThreads), false);                    \
+        if (!launched) TD_ENUM_LAUNCH(DS, CS, PF, kEnumThreads, true);   /* big tables: the wide CTA's stages do not fit */ \
         if (!launched) return TD_ERR_CUDA;                                                                               \
     } while (0)
     if (pf) { if (cs) TD_ENUM_CASE(true, true, (K == 4)); else TD_ENUM_CASE(true, false, (K == 4)); }

@@ -87,6 +87,35 @@ def _h2d_i32(a, pinned: bool = True) -> torch.Tensor:
     return t
 
 
+def _h2d_i32_many(arrays) -> list:
+    """Several small host arrays -> int32 CUDA tensors through ONE pinned staging buffer and ONE asynchronous copy (each
+    array starts on a 16-byte boundary: the pool kernels stage their tables with bulk copies).  The per-copy cost of a
+    few-KB transfer is its fixed latency, not its bytes."""
+    arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.int32)) for a in arrays]
+    offs, total = [], 0
+    for arr in arrs:
+        offs.append(total)
+        total += (arr.size + 3) & ~3
+    if total == 0 or total > (1 << 22) or any(arr.size == 0 for arr in arrs):
+        return [_h2d_i32(arr) for arr in arrs]
+    COPIED["h2d"] += sum(arr.nbytes for arr in arrs)
+    bucket = 1 << max(8, int(total - 1).bit_length())
+    slot = _PINNED.get(("many", bucket))
+    if slot is None:
+        slot = {"buf": torch.empty(bucket, dtype=torch.int32).pin_memory(), "ev": None}
+        _PINNED[("many", bucket)] = slot
+    if slot["ev"] is not None:
+        slot["ev"].synchronize()
+    host = slot["buf"].numpy()
+    for arr, off in zip(arrs, offs):
+        host[off: off + arr.size] = arr.reshape(-1)
+    dev = slot["buf"][:total].to("cuda", non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    slot["ev"] = ev
+    return [dev[off: off + arr.size].reshape(arr.shape) for arr, off in zip(arrs, offs)]
+
+
 class Engine:
     """Device-pointer front end: torch CUDA tensors in, torch CUDA tensors out, workspaces cached
     per (operation, size) so that steady-state calls allocate nothing."""
@@ -567,8 +596,7 @@ def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
     eng = engine()
     dem_np = np.asarray(demand, dtype=np.int32).reshape(-1, 5)
     n = dem_np.shape[0]
-    dem = _h2d_i32(dem_np)
-    d = _h2d_i32(dist)
+    dem, d = _h2d_i32_many([dem_np, dist])                # one pinned staging buffer, one copy
     stats = {"evaluated": 0, "feasible": 0, "kept_per_shard": [], "rounds": 0}
     fast_key = ("pool_single_pass_ok", n, pool_size, n_shards)
     if n_shards <= 64 and eng._ws.get(fast_key):

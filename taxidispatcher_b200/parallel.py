@@ -138,8 +138,7 @@ def _find_pool_sharded_device(dem: np.ndarray, dist_table, pool_size: int, n_sha
     n = dem.shape[0]
     cap = n // 2 + 1
     slots = (n_shards + w - 1) // w
-    dem_d = dispatch._h2d_i32(dem)
-    dist_d = dispatch._h2d_i32(dist_table)
+    dem_d, dist_d = dispatch._h2d_i32_many([dem, dist_table])
     key = (w, n_shards, n, dev.index)
     if key not in _SLOT_SHARD:      # buffers + the logical shard of every (rank, slot); padding slots keep count 0 for ever
         ids = []

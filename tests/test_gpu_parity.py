@@ -258,6 +258,26 @@ def test_pool_k4_pruning_bounds_fuzz(td):
         assert np.array_equal(plans, oplans), (case, kind, S, n)
 
 
+@pytest.mark.parametrize("S", [64, 65, 100, 128, 129])
+def test_pool_k4_closure_tile_sizes(td, S):
+    """the shortest-path closure runs in 4 x 4 register tiles up to 64 stands and 8 x 8 up to 128; above that the bound
+    is switched off.  Non-metric tables with cheap detours through a few hub stands make D* differ from D."""
+    rng = np.random.default_rng(1000 + S)
+    dist = rng.integers(4, 40, (S, S)).astype(np.int32)
+    hubs = rng.choice(S, 5, replace=False)
+    dist[hubs, :] = rng.integers(0, 3, (5, S))
+    dist[:, hubs] = rng.integers(0, 3, (S, 5))
+    np.fill_diagonal(dist, 0)
+    n = 44
+    dem = np.stack([np.arange(n), rng.integers(0, S, n), rng.integers(0, S, n), rng.integers(0, 30, n),
+                    rng.integers(0, 200, n)], axis=1).astype(np.int32)
+    plans, st = td.find_pool(dem, dist, 4, 0, 1)
+    oplans, ost = pool_ref.find(dem, dist, 4, 0, 1)
+    assert {q: st[q] for q in ost} == ost
+    assert np.array_equal(plans, oplans)
+    assert ost["feasible"] > 0
+
+
 @pytest.mark.parametrize("k", [2, 3, 4])
 def test_pool_large_costs_take_the_two_level_keys(td, k):
     """plan costs >= 255 fall into the open-ended histogram bucket: the selection cannot pack (cost, rank) into one
