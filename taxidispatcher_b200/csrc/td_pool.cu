@@ -1245,6 +1245,7 @@ pool_emit_kernel(const PoolRec *__restrict__ kept_all, const PoolCtrl *ctrl, int
 // compaction runs in shared memory: a bitonic sort of the 64-bit scan keys, dominance rounds with the SORTED POSITION as
 // a 32-bit key (native shared-memory atomicMin on a per-customer table), a block scan for the output positions.
 // More rows take the general path (ranks by counting, state in the global workspace).
+constexpr int kMergeSlots = 64;   // pool_merge ranks by binary search when it has at most this many (sorted) slots
 constexpr int kMergeFast = 8192;
 __global__ void __launch_bounds__(1024)
 pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, const int32_t *__restrict__ counts, int cap,
@@ -1259,27 +1260,52 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, 
     const int slot_rows = cap + headed;
     const int total = n_slots * cap;
     auto row_ptr = [&](int ridx) { return plans + size_t(ridx) * TD_POOL_REC_W; };   // ridx: row index in the padded layout
-    if (tid == 0) s_m = 0;
+    // Compaction.  Up to kMergeSlots slots: slot-major order (offsets = prefix sums of the counts), so that every slot's
+    // rows stay a contiguous run -- the producer (pool_emit) writes them in ascending (cost, rank) order and the merge
+    // below then needs no sort, only a rank by binary searches.  More slots: arrival order, sorted afterwards.
+    __shared__ int s_off[kMergeSlots + 1];
+    __shared__ int s_unsorted;
+    const bool by_slot = n_slots <= kMergeSlots;
+    auto count_of = [&](int slot) { return counts ? counts[slot] : (headed ? plans[size_t(slot) * slot_rows * TD_POOL_REC_W] : cap); };
+    if (tid == 0) { s_m = 0; s_unsorted = 0; }
+    if (by_slot && tid < 32) {   // one warp: exclusive scan of the (clamped) counts
+        int run = 0;
+        for (int b0 = 0; b0 < n_slots; b0 += 32) {
+            const int slot = b0 + tid;
+            int c = slot < n_slots ? count_of(slot) : 0;
+            c = c < 0 ? 0 : (c > cap ? cap : c);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+            if (slot < n_slots) s_off[slot] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) s_off[n_slots] = run;
+    }
     __syncthreads();
     for (int base = 0; base < total; base += blockDim.x) {
         const int i = base + tid;
         bool ok = false;
         long long pos = 0;
-        int ridx = 0;
+        int ridx = 0, slot = 0, r = 0;
         if (i < total) {
-            const int slot = i / cap, r = i % cap;
-            const int cnt = counts ? counts[slot] : (headed ? plans[size_t(slot) * slot_rows * TD_POOL_REC_W] : cap);
+            slot = i / cap; r = i % cap;
+            const int cnt = count_of(slot);
             ok = r < cnt;
             pos = (long long)(slot_shard ? slot_shard[slot] : slot) * cap + r;
             ridx = slot * slot_rows + headed + r;
         }
         if (ok) {
-            const int c = atomicAdd(&s_m, 1);
+            const int c = by_slot ? s_off[slot] + r : atomicAdd(&s_m, 1);
             const unsigned long long costpart = K == TD_POOL_MAX_IN_POOL ? (unsigned long long)(unsigned)row_ptr(ridx)[8] : 0ull;
             ckey[c] = (costpart << 32) | (unsigned long long)pos;   // pos < 2^32 (total <= 2^24 rows)
             crow[c] = ridx;
+            // a slot whose rows do not ascend (a caller's own rows) sends the merge through the sort
+            if (by_slot && K == TD_POOL_MAX_IN_POOL && r > 0 && (unsigned)row_ptr(ridx - 1)[8] > (unsigned)costpart) s_unsorted = 1;
         }
     }
+    __syncthreads();
+    if (by_slot && tid == 0) s_m = s_off[n_slots];
     __syncthreads();
     const int m = s_m;
     if (m == 0) { if (tid == 0) *n_plans_out = 0; return; }
@@ -1292,6 +1318,30 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, 
         uint8_t *st = reinterpret_cast<uint8_t *>(own + n);
         int P = 1;
         while (P < m) P <<= 1;
+        if (by_slot && !s_unsorted) {
+            // every slot is an ascending run: sorted position = own index in the run + the number of smaller keys in every
+            // other run (binary searches in shared memory; keys are unique) -- no sort, two block barriers
+            unsigned long long *ukeys = reinterpret_cast<unsigned long long *>(cu);   // cu[] is filled after this step
+            for (int i = tid; i < m; i += blockDim.x) ukeys[i] = ckey[i];
+            __syncthreads();
+            for (int i = tid; i < m; i += blockDim.x) {
+                const unsigned long long key = ukeys[i];
+                int rank = 0;
+                for (int sl = 0; sl < n_slots; ++sl) {
+                    int lo = s_off[sl], hi = s_off[sl + 1];
+                    if (i >= lo && i < hi) { rank += i - lo; continue; }
+                    const int first = lo;
+                    while (lo < hi) {   // lower bound of key in ukeys[lo, hi)
+                        const int mid = (lo + hi) >> 1;
+                        if (ukeys[mid] < key) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo - first;
+                }
+                keys[rank] = key;
+                rows[rank] = crow[i];
+            }
+            __syncthreads();
+        } else {
         for (int i = tid; i < P; i += blockDim.x) {
             keys[i] = i < m ? ckey[i] : ~0ull;
             rows[i] = i < m ? crow[i] : -1;
@@ -1312,6 +1362,7 @@ pool_merge_kernel(const int32_t *__restrict__ plans, int n_slots, int n, int K, 
                 }
                 __syncthreads();
             }
+        }
         for (int i = tid; i < m; i += blockDim.x) {
             st[i] = 0;
             const int32_t *row = row_ptr(rows[i]);

@@ -702,6 +702,39 @@ def test_pool_1200_customers_golden_single_pass_and_windows(td):
     assert st[0].passes > 1
 
 
+def test_pool_merge_padded_sorted_unsorted_and_many_slots(td):
+    """td_pool_merge_padded ranks by binary search when every slot is an ascending run (what pool_emit produces), sorts
+    when a caller hands in rows in another order, and takes the arrival-order compaction above 64 slots: all three must
+    equal the restated merge (findpool.c:83-108) of the same rows."""
+    import torch
+    eng = td.engine()
+    dem = g.pool_demand(300, seed=77)
+    dist = g.stand_distances(50)
+    dd, ds = torch.from_numpy(dem).cuda(), torch.from_numpy(dist).cuda()
+    rng = np.random.default_rng(5)
+    for n_shards in (8, 70):
+        outs, cnts = [], []
+        for b in range(0, n_shards, 64):
+            c = min(64, n_shards - b)
+            out, cnt, st = eng.pool_find_shards(dd, ds, 4, b, c, n_shards)
+            outs.append(out.clone()); cnts.append(cnt.clone())
+        out, cnt = torch.cat(outs, 0), torch.cat(cnts, 0)
+        counts = cnt.cpu().numpy()
+        host = out.cpu().numpy()
+        want = pool_ref.merge([host[s_, : counts[s_]] for s_ in range(n_shards)], 300, 4)
+        merged, mc = eng.pool_merge_padded(out, cnt, None, 300, 4)
+        assert merged[: int(mc.item())].cpu().numpy().tolist() == want.tolist(), n_shards
+        # the same rows with one slot's rows permuted: the position in the input breaks ties, so the answer is the merge of
+        # the permuted rows
+        big = int(np.argmax(counts))
+        perm = rng.permutation(int(counts[big]))
+        host2 = host.copy()
+        host2[big, : counts[big]] = host[big, : counts[big]][perm]
+        want2 = pool_ref.merge([host2[s_, : counts[s_]] for s_ in range(n_shards)], 300, 4)
+        merged2, mc2 = eng.pool_merge_padded(torch.from_numpy(host2).cuda(), cnt, None, 300, 4)
+        assert merged2[: int(mc2.item())].cpu().numpy().tolist() == want2.tolist(), n_shards
+
+
 def test_pool_headed_blocks_and_steady_state_path(td):
     """Headed blocks (survivors + count + counters in one buffer, the layout of the multi-GPU gather) and the merge on
     them: identical to the plain entry points, on config 3 and on a K = 2 / K = 3 case; find_pool_all takes the headed
