@@ -20,7 +20,8 @@
 //                      "cumulative pickup distance w + D(s,F[c]) <= W[c]" turns into "c is in the
 //                      first cnt[s][w] entries of list[s]": the next pickup level is a contiguous
 //                      prefix, no search, no test.
-//   pool_item_offsets  work items = (leader, position in list[F[leader]]) for K >= 3, leader for K = 2
+//   (item offsets)     work items = (leader, position in list[F[leader]]) for K >= 3, leader for K = 2; computed by the
+//                      CTA of pool_build_lists that finishes last
 //   pool_enum<K>       one warp per item; outer pickup levels are warp-uniform loops, the LAST
 //                      pickup level is spread over the 32 lanes; each lane evaluates all K! drop-off
 //                      orders of its tuple in registers (fully unrolled, shared prefixes CSE'd).
@@ -79,10 +80,11 @@ struct PoolCtrl {
     unsigned long long evaluated[kMaxSlots], feasible[kMaxSlots];  // per logical shard of this call
     unsigned int n_kept[kMaxSlots];
     unsigned int total_rounds;
-    unsigned int n_items;         // work items of the enumeration (set once by pool_item_offsets)
-    unsigned int closure_ok;      // pool_closure_kernel: the shortest-path closure of the stand table is usable as a lower bound
+    unsigned int n_items;         // work items of the enumeration (set once by pool_build_lists)
+    unsigned int closure_ok;      // pool_closure: the shortest-path closure of the stand table is usable as a lower bound
     unsigned int bad_input;       // a stand index outside the table, or (K = 4) a stand distance above kDistLimit (the x32
                                   // fixed-point evaluation would overflow): the call reports TD_ERR_INVALID / count -1
+    unsigned int lists_done;      // CTAs of pool_build_lists that have finished (the last one computes the item offsets)
     unsigned int pass_begin_marker;  // ---- everything below is zeroed before every enumeration pass ----
     unsigned int n_records;       // slots reserved in the record list
     unsigned int item_counter;
@@ -112,9 +114,8 @@ __device__ __forceinline__ void split_rank(unsigned long long r, int p[4], int &
 
 // ---- prep ----------------------------------------------------------------------------------------
 __device__ __forceinline__ int4 scale_cust_rt(int4 c, int sh);
-__global__ void pool_prep_cust_kernel(const int32_t *__restrict__ demand, int n, const int32_t *__restrict__ dist,
-                                      int S, int4 *cust, int4 *cust_s, int sh, PoolCtrl *ctrl) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pool_prep_cust(int c, const int32_t *__restrict__ demand, int n, const int32_t *__restrict__ dist,
+                                               int S, int4 *cust, int4 *cust_s, int sh, PoolCtrl *ctrl) {
     if (c >= n) return;
     int f = demand[c * 5 + 1], t = demand[c * 5 + 2];
     const int w = demand[c * 5 + 3], l = demand[c * 5 + 4];
@@ -137,7 +138,8 @@ __global__ void pool_prep_cust_kernel(const int32_t *__restrict__ demand, int n,
 // one CTA per stand: counting sort of the customers reachable from this stand by slack, descending
 __global__ void __launch_bounds__(256)
 pool_build_lists_kernel(const int4 *__restrict__ cust, int n, const int32_t *__restrict__ dist, int S,
-                        int32_t *list, int32_t *slack_out, int32_t *cnt) {
+                        int32_t *list, int32_t *slack_out, int32_t *cnt, int start, int stop, int pool_size,
+                        unsigned int *item_off, PoolCtrl *ctrl) {
     __shared__ int hist[kTbl];
     __shared__ int offs[kTbl];
     const int s = blockIdx.x;
@@ -167,30 +169,39 @@ pool_build_lists_kernel(const int4 *__restrict__ cust, int n, const int32_t *__r
             slack_out[size_t(s) * n + pos] = sl;
         }
     }
-}
-
-// items per leader (exclusive prefix).  K >= 3: one item per (leader, first-level candidate).
-__global__ void __launch_bounds__(1024)
-pool_item_offsets_kernel(const int4 *__restrict__ cust, const int32_t *__restrict__ cnt, int start, int stop,
-                         int pool_size, unsigned int *item_off, PoolCtrl *ctrl) {
-    __shared__ unsigned s_part[1024];
+    // ---- items per leader (exclusive prefix; K >= 3: one item per (leader, first-level candidate)), by the CTA that
+    // finishes last: it needs cnt[] of every stand, and a kernel of its own would cost a launch for a few microseconds
+    __shared__ bool s_last;
+    __shared__ unsigned s_part[256];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                         // this CTA's cnt[] before the ticket
+        s_last = atomicAdd(&ctrl->lists_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     const int nl = stop - start;
-    const int chunk = (nl + 1023) / 1024;
+    const int chunk = (nl + 255) / 256;
     const int lo = min(int(threadIdx.x) * chunk, nl), hi = min(lo + chunk, nl);
     auto items_of = [&](int p0) -> unsigned {
         const int4 r = cust[p0];
         if (r.w < 0) return 0u;                                  // pool_n.c:172 at level 0
-        return pool_size >= 3 ? unsigned(cnt[size_t(r.x) * kTbl + 0]) : 1u;
+        return pool_size >= 3 ? unsigned(__ldcg(cnt + size_t(r.x) * kTbl + 0)) : 1u;   // written by other CTAs: L2
     };
     unsigned sum = 0;
     for (int t = lo; t < hi; ++t) sum += items_of(start + t);
     s_part[threadIdx.x] = sum;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned run = 0;
-        for (int t = 0; t < 1024; ++t) { const unsigned v = s_part[t]; s_part[t] = run; run += v; }
-        item_off[nl] = run;
-        ctrl->n_items = run;
+    if (threadIdx.x < 32) {   // exclusive scan of the 256 partial sums: 8 per lane, warp scan of the lane sums
+        unsigned mine = 0;
+        for (int k = 0; k < 8; ++k) mine += s_part[threadIdx.x * 8 + k];
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (threadIdx.x >= o) incl += v; }
+        unsigned acc = incl - mine;
+        for (int k = 0; k < 8; ++k) { const unsigned v = s_part[threadIdx.x * 8 + k]; s_part[threadIdx.x * 8 + k] = acc; acc += v; }
+        if (threadIdx.x == 31) { item_off[nl] = incl; ctrl->n_items = incl; }
     }
     __syncthreads();
     unsigned run = s_part[threadIdx.x];
@@ -202,10 +213,10 @@ pool_item_offsets_kernel(const int4 *__restrict__ cust, const int32_t *__restric
 // in the record list) or an entry above kDistLimit (K = 4: the x32 fixed point of eval4s needs 7 legs x 32 < 2^31; K = 2, 3:
 // the (cost << 5 | permutation) order key needs 5 legs < 2^26) is refused with TD_ERR_INVALID, never clamped.
 constexpr int kDistLimit = 1 << 22;
-__global__ void __launch_bounds__(256)
-pool_check_table_kernel(const int32_t *__restrict__ dist, long long cells, PoolCtrl *ctrl, int32_t *dist_s, int sh) {
+__device__ __forceinline__ void pool_check_table(int block, int blocks, const int32_t *__restrict__ dist, long long cells,
+                                                 PoolCtrl *ctrl, int32_t *dist_s, int sh) {
     int bad = 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = block * (long long)blockDim.x + threadIdx.x; i < cells; i += (long long)blocks * blockDim.x) {
         const int v = dist[i];
         bad |= (v < 0) | (v > kDistLimit);
         if (dist_s) dist_s[i] = v << sh;       // the copy the enumeration stages by bulk copy (small tables only)
@@ -261,8 +272,7 @@ __device__ __forceinline__ void closure_steps(int S, int32_t *s_d, int32_t *s_li
         }
 }
 
-__global__ void __launch_bounds__(256)
-pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict__ dclose, int sh, PoolCtrl *ctrl) {
+__device__ __forceinline__ void pool_closure(const int32_t *__restrict__ dist, int S, int32_t *__restrict__ dclose, int sh, PoolCtrl *ctrl) {
     extern __shared__ int32_t s_d[];
     __shared__ int32_t s_line[2][2][kPfMaxStands];
     const int cells = S * S;
@@ -283,6 +293,18 @@ pool_closure_kernel(const int32_t *__restrict__ dist, int S, int32_t *__restrict
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) dclose[i] = (s_d[i] > kDistLimit ? kDistLimit : s_d[i]) << sh;   // D* <= D <= limit on accepted tables
     if (threadIdx.x == 0) ctrl->closure_ok = neg ? 0u : 1u;
+}
+
+// The three independent input passes of a call in ONE launch (a launch costs more than any of them): CTA 0 computes the
+// closure (the longest, so it starts first), the next check_blocks CTAs check / scale the stand table, the rest prepare the
+// customer records.
+__global__ void __launch_bounds__(256)
+pool_prepare_kernel(const int32_t *__restrict__ demand, int n, const int32_t *__restrict__ dist, int S, int4 *cust, int4 *cust_s,
+                    int sh, PoolCtrl *ctrl, int32_t *dist_s, int32_t *dclose, int closure_blocks, int check_blocks) {
+    const int b = blockIdx.x;
+    if (b < closure_blocks) pool_closure(dist, S, dclose, sh, ctrl);
+    else if (b < closure_blocks + check_blocks) pool_check_table(b - closure_blocks, check_blocks, dist, (long long)S * S, ctrl, dist_s, sh);
+    else pool_prep_cust((b - closure_blocks - check_blocks) * blockDim.x + threadIdx.x, demand, n, dist, S, cust, cust_s, sh, ctrl);
 }
 
 // ---- enumeration ---------------------------------------------------------------------------------
@@ -433,7 +455,7 @@ __device__ __forceinline__ void eval3(const int e[3], const int t[3][3], const i
 }
 
 // kPF (K = 4 with the stand table in shared memory): the closure D* is staged next to the table and the lower bound of
-// pool_closure_kernel prunes pickup prefixes at the third and at the last pickup level.
+// pool_closure prunes pickup prefixes at the third and at the last pickup level.
 // kThr: threads per CTA.  256 when several CTAs fit an SM; when the staged tables leave room for ONE CTA only (5000 customers:
 // 80 KB of customer records), a 768-thread CTA keeps 24 warps per SM busy instead of 8 (ncu r02n: 11 % warps active, 40 % issue).
 template <int K, bool kDistSmem, bool kCustSmem, bool kPF, int kThr>
@@ -1726,26 +1748,21 @@ static int pool_find_shards_impl(const int32_t *demand, int n, const int32_t *di
 
     TD_CUDA_TRY(cudaMemsetAsync(w.ctrl, 0, sizeof(PoolCtrl), st));
     const int sh = pool_size == 4 ? kSh4 : 0;                                  // fixed point of the enumeration's evaluation
-    pool_prep_cust_kernel<<<(n + 255) / 256, 256, 0, st>>>(demand, n, dist, n_stands, w.cust, w.cust_s, sh, w.ctrl);
-    TD_LAUNCH_CHECK();
-    pool_build_lists_kernel<<<n_stands, 256, 0, st>>>(w.cust, n, dist, n_stands, w.list, w.slack, w.cnt);
-    TD_LAUNCH_CHECK();
-    pool_item_offsets_kernel<<<1, 1024, 0, st>>>(w.cust, w.cnt, start, stop, pool_size, w.item_off, w.ctrl);
-    TD_LAUNCH_CHECK();
+    const bool closure = pool_size == 4 && n_stands <= kPfMaxStands;
     {
         const long long cells = (long long)n_stands * n_stands;
         const long long want = (cells + 256 * 16 - 1) / (256 * 16);
-        const int grid = int(want < 1 ? 1 : (want > 4LL * device_sm_count() ? 4LL * device_sm_count() : want));
-        pool_check_table_kernel<<<grid, 256, 0, st>>>(dist, cells, w.ctrl, n_stands <= kPfMaxStands ? w.dist_s : nullptr, sh);
+        const int check_blocks = int(want < 1 ? 1 : (want > 4LL * device_sm_count() ? 4LL * device_sm_count() : want));
+        const size_t cl_smem = closure ? size_t(n_stands) * n_stands * 4 : 0;
+        TD_CUDA_TRY(cudaFuncSetAttribute(pool_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(64 * 1024)));
+        pool_prepare_kernel<<<(closure ? 1 : 0) + check_blocks + (n + 255) / 256, 256, cl_smem, st>>>(
+            demand, n, dist, n_stands, w.cust, w.cust_s, sh, w.ctrl, n_stands <= kPfMaxStands ? w.dist_s : nullptr, w.dclose,
+            closure ? 1 : 0, check_blocks);
         TD_LAUNCH_CHECK();
     }
-    const bool closure = pool_size == 4 && n_stands <= kPfMaxStands;
-    if (closure) {
-        const size_t cl_smem = size_t(n_stands) * n_stands * 4;
-        TD_CUDA_TRY(cudaFuncSetAttribute(pool_closure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(64 * 1024)));
-        pool_closure_kernel<<<1, 256, cl_smem, st>>>(dist, n_stands, w.dclose, sh, w.ctrl);
-        TD_LAUNCH_CHECK();
-    }
+    pool_build_lists_kernel<<<n_stands, 256, 0, st>>>(w.cust, n, dist, n_stands, w.list, w.slack, w.cnt, start, stop, pool_size,
+                                                      w.item_off, w.ctrl);
+    TD_LAUNCH_CHECK();
 
     const int sms = device_sm_count();
     int sel_per_sm = 0;
