@@ -428,7 +428,7 @@ def main():
             return dispatch.find_pool_all(dem_np, dist_np, POOL_K)
         return parallel.find_pool_sharded(dem_np, dist_np, POOL_K)
 
-    for _ in range(3):     # warm-up: the first call sizes the record list, the second one reallocates the workspace
+    for _ in range(5):     # warm-up: call 1 sizes the record list, 2-3 take the asynchronous path, 4-5 the captured graph
         e2e_step()
     barrier()
     copied0 = dict(dispatch.COPIED)
@@ -528,6 +528,7 @@ def main():
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "components": components}
         print(json.dumps(line), flush=True)
+    dispatch.release_pool_graphs()
     if world > 1:
         dist.destroy_process_group()
 

@@ -743,11 +743,32 @@ def test_pool_headed_blocks_and_steady_state_path(td):
     gold = load_golden("pool722.json")
     eng = td.engine()
     dem_np, dist_np = g.pool_demand(), g.stand_distances(50)
-    for rep in range(3):
+    from taxidispatcher_b200 import dispatch
+    for rep in range(6):       # 1: cost-window path, 2-3: asynchronous headed path, 4-6: the captured graph (PoolJobGraph)
         merged, st = td.find_pool_all(dem_np, dist_np, 4)
         assert merged.tolist() == gold["merged"], rep
         assert st["evaluated"] == sum(g.POOL722_EVALUATED) and st["feasible"] == sum(g.POOL722_FEASIBLE)
         assert st["kept_per_shard"] == g.POOL722_KEPT and st["kept"] == 110
+    gkey = ("all", 722, 50, 4, 8, eng.device.index)
+    assert isinstance(dispatch._POOL_GRAPHS.get(gkey), dispatch.PoolJobGraph)
+    # another input of the same shape through the same graph, checked against the piecewise path
+    dem2 = g.pool_demand(722, seed=9)
+    got, st2 = td.find_pool_all(dem2, dist_np, 4)
+    graph = dispatch._POOL_GRAPHS.pop(gkey, None)          # (None: dem2 outgrew the record list and dropped the graph)
+    want, st_want = td.find_pool_all(dem2, dist_np, 4)
+    assert got.tolist() == want.tolist()
+    assert {k_: st2[k_] for k_ in ("evaluated", "feasible", "kept_per_shard", "kept")} == \
+           {k_: st_want[k_] for k_ in ("evaluated", "feasible", "kept_per_shard", "kept")}
+    if graph is None:
+        for rep in range(4):
+            td.find_pool_all(dem_np, dist_np, 4)
+        graph = dispatch._POOL_GRAPHS[gkey]
+    dispatch._POOL_GRAPHS[gkey] = graph
+    # a bigger job reallocates the engine's workspaces: the graph notices and the next call rebuilds its way up again
+    td.find_pool_all(g.pool_demand(900, seed=3), dist_np, 4)
+    ok_before = graph.valid()
+    merged, st = td.find_pool_all(dem_np, dist_np, 4)
+    assert merged.tolist() == gold["merged"] and (ok_before or dispatch._POOL_GRAPHS.get(gkey) is not graph)
     dem, dist = torch.from_numpy(dem_np).cuda(), torch.from_numpy(dist_np).cuda()
     cap = 722 // 2 + 1
     # two "ranks" with 5 + 3 shards, padded to 5 slots each, gathered in rank order: the multi-GPU layout on one device
@@ -768,7 +789,7 @@ def test_pool_headed_blocks_and_steady_state_path(td):
     case = load_golden("pool_small.json")
     for c in case[6:12]:
         d_np = np.array(c["demand"], dtype=np.int32)
-        for rep in range(2):
+        for rep in range(5):                       # the last two calls run the captured graph
             merged, st = td.find_pool_all(d_np, g.stand_distances(c["n_stands"]), c["pool_size"])
             assert merged.tolist() == c["merged"], (c["label"], rep)
 
