@@ -698,6 +698,15 @@ def release_pool_graphs():
             torch.cuda.synchronize()
 
 
+def _capture_pool_job(*args, **kwargs):
+    """PoolJobGraph, or a counter value that never reaches the capture threshold again when the capture fails (the
+    piecewise path keeps serving the shape; the result of the current call has been computed already)."""
+    try:
+        return PoolJobGraph(*args, **kwargs)
+    except Exception:                                     # noqa: BLE001 -- any capture failure means "no graph", never "no result"
+        return -(1 << 30)
+
+
 def _pool_graphs_enabled() -> bool:
     return os.environ.get("TD_POOL_GRAPH", "1") != "0"
 
@@ -739,7 +748,7 @@ def find_pool_all(demand, dist, pool_size: int, n_shards: int = 8):
                          kept=len(plans))
             if _pool_graphs_enabled() and n > 0 and dist_np.ndim == 2:
                 seen = _POOL_GRAPHS.get(gkey, 0) + 1      # second success of the shape: capture the job
-                _POOL_GRAPHS[gkey] = seen if seen < 2 else PoolJobGraph(eng, n, dist_np.shape[0], pool_size, n_shards, 0, n_shards)
+                _POOL_GRAPHS[gkey] = seen if seen < 2 else _capture_pool_job(eng, n, dist_np.shape[0], pool_size, n_shards, 0, n_shards)
             return plans, stats
         eng._ws[fast_key] = False                         # input outgrew the record list: cost windows below
         _POOL_GRAPHS.pop(gkey, None)

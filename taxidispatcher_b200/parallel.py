@@ -181,7 +181,7 @@ def _find_pool_sharded_device(dem: np.ndarray, dist_table, pool_size: int, n_sha
         return None
     if dispatch._pool_graphs_enabled() and n > 0 and dist_np.ndim == 2:
         seen = dispatch._POOL_GRAPHS.get(gkey, 0) + 1          # second success of the shape: capture the job (every rank does)
-        dispatch._POOL_GRAPHS[gkey] = seen if seen < 2 else dispatch.PoolJobGraph(
+        dispatch._POOL_GRAPHS[gkey] = seen if seen < 2 else dispatch._capture_pool_job(
             eng, n, dist_np.shape[0], pool_size, n_shards, mine[0] if mine else 0, len(mine),
             gather=(dist.all_gather_into_tensor, w), slots=slots, slot_shard=slot_shard)
     return result(plans, counts, ev, fe)
