@@ -47,6 +47,21 @@ class CudaBackend:
         self.eng = dispatch.engine()
         self.times = {"pool": 0.0, "cost": 0.0, "lcm": 0.0, "solve": 0.0}
         self._cost_dev = None      # (id of the host array handed out, device tensor)
+        self._dist_dev = None      # (host stand table, device copy): the table does not change during a replay
+        self._pin = [None, None]   # two pinned read-back buffers, used alternately (a step holds at most two cost matrices)
+        self._pin_i = 0
+
+    def _read_back(self, dev):
+        """Device int32 tensor -> numpy through a reused pinned buffer (a 1300 x 1300 matrix per step: pageable read-backs
+        were most of the replay's host time).  The view stays valid until the second next call."""
+        n = dev.numel()
+        buf = self._pin[self._pin_i]
+        if buf is None or buf.numel() < n:
+            buf = self._pin[self._pin_i] = self.torch.empty(max(n, 1 << 21), dtype=dev.dtype).pin_memory()
+        self._pin_i ^= 1
+        view = buf[:n].view(dev.shape)
+        view.copy_(dev)                                   # blocking copy into pinned memory
+        return view.numpy()
 
     def _device_cost(self, cost):
         if self._cost_dev is not None and self._cost_dev[0] is cost:
@@ -66,9 +81,11 @@ class CudaBackend:
             return np.zeros((0, 0), np.int32)
         h2d = self.d._h2d_i32
         empty = self.torch.empty(0, dtype=self.torch.int32, device=self.eng.device)
-        dev = self.eng.cost_matrix(h2d(dist), h2d(cab_to) if len(cab_to) else empty,
+        if self._dist_dev is None or self._dist_dev[0] is not dist:
+            self._dist_dev = (dist, h2d(dist))
+        dev = self.eng.cost_matrix(self._dist_dev[1], h2d(cab_to) if len(cab_to) else empty,
                                    h2d(cust_from) if len(cust_from) else empty, BIG_COST, DROP_TIME)
-        host = dev.cpu().numpy()
+        host = self._read_back(dev)
         self._cost_dev = (host, dev)
         self.times["cost"] += time.perf_counter() - t0
         return host
@@ -152,24 +169,26 @@ class Simulator:
     # ---- Simulator.java:220-254 ----------------------------------------------------------------------
     def check_if_cab_at_destination(self, t: int):
         cabs, dist = self.cabs, self.dist
-        for c in range(self.n_cabs):
-            if cabs[c, FROM] != cabs[c, TO] and dist[cabs[c, FROM], cabs[c, TO]] == t - cabs[c, TIME_STARTED]:
-                if cabs[c, CLNT_ON_BOARD] == 0:                      # was heading to its customer
-                    d = self.id_to_row.get(int(cabs[c, CLNT_ASSIGNED]))
-                    if d is not None:
-                        self.d_cab[d] = cabs[c, ID]
-                        self.d_pickup_t[d] = t
-                        self.m.total_pickup_numb += 1
-                        cabs[c, FROM] = self.d_from[d]
-                        cabs[c, TO] = self.d_to[d] if self.d_pool_clnt[d] == -1 else cheat_a_bit(int(self.d_from[d]), int(self.d_pool_cost[d]), self.n_stands)
-                        cabs[c, CLNT_ASSIGNED] = self.d_id[d]
-                        cabs[c, CLNT_ON_BOARD] = 1
-                        cabs[c, TIME_STARTED] = t
-                else:                                                # a trip has just been completed
-                    cabs[c, FROM] = cabs[c, TO]
-                    cabs[c, CLNT_ASSIGNED] = -1
-                    cabs[c, CLNT_ON_BOARD] = 0
-                    cabs[c, TIME_STARTED] = -1
+        # the arrival test for all cabs at once; a cab's update touches only its own row and its own customer, so the
+        # arrived cabs can be handled in index order afterwards (same order as the reference's loop)
+        arrived = np.nonzero((cabs[:, FROM] != cabs[:, TO]) & (dist[cabs[:, FROM], cabs[:, TO]] == t - cabs[:, TIME_STARTED]))[0]
+        for c in arrived.tolist():
+            if cabs[c, CLNT_ON_BOARD] == 0:                      # was heading to its customer
+                d = self.id_to_row.get(int(cabs[c, CLNT_ASSIGNED]))
+                if d is not None:
+                    self.d_cab[d] = cabs[c, ID]
+                    self.d_pickup_t[d] = t
+                    self.m.total_pickup_numb += 1
+                    cabs[c, FROM] = self.d_from[d]
+                    cabs[c, TO] = self.d_to[d] if self.d_pool_clnt[d] == -1 else cheat_a_bit(int(self.d_from[d]), int(self.d_pool_cost[d]), self.n_stands)
+                    cabs[c, CLNT_ASSIGNED] = self.d_id[d]
+                    cabs[c, CLNT_ON_BOARD] = 1
+                    cabs[c, TIME_STARTED] = t
+            else:                                                # a trip has just been completed
+                cabs[c, FROM] = cabs[c, TO]
+                cabs[c, CLNT_ASSIGNED] = -1
+                cabs[c, CLNT_ON_BOARD] = 0
+                cabs[c, TIME_STARTED] = -1
 
     # ---- Simulator.java:329-355 ----------------------------------------------------------------------
     def create_temp_demand(self, t: int) -> List[TempDemand]:
@@ -186,17 +205,18 @@ class Simulator:
             return []
         reach = (self.dist[free_to] < DROP_TIME).any(0)                             # per stand
         keep = rest[reach[self.d_from[rest]]]
-        return [TempDemand(int(self.d_id[d]), int(self.d_from[d]), int(self.d_to[d])) for d in keep]
+        return [TempDemand(i, f, t_) for i, f, t_ in zip(self.d_id[keep].tolist(), self.d_from[keep].tolist(), self.d_to[keep].tolist())]
 
     # ---- Simulator.java:358-372 ----------------------------------------------------------------------
     def create_temp_supply(self) -> List[Tuple[int, int, int]]:
-        un_from = np.unique(self.d_from[self.d_cab == -1])                          # the WHOLE file, future arrivals too
-        if len(un_from) == 0:
+        un_from = np.zeros(self.n_stands, bool)                                     # the WHOLE file, future arrivals too
+        un_from[self.d_from[self.d_cab == -1]] = True
+        if not un_from.any():
             return []
         reach = (self.dist[:, un_from] < DROP_TIME).any(1)
         c = self.cabs
         sel = np.nonzero((c[:, FROM] == c[:, TO]) & (c[:, CLNT_ASSIGNED] == -1) & reach[c[:, TO]])[0]
-        return [(int(c[i, ID]), int(c[i, FROM]), int(c[i, TO])) for i in sel]
+        return list(zip(c[sel, ID].tolist(), c[sel, FROM].tolist(), c[sel, TO].tolist()))
 
     # ---- Simulator.java:681-758 + 760-784 ------------------------------------------------------------
     def find_and_analyze_pool(self, temp_demand: List[TempDemand]) -> List[TempDemand]:
@@ -208,19 +228,17 @@ class Simulator:
         self.m.max_POOL_size = max(self.m.max_POOL_size, len(pairs))
         self.m.max_POOL_MEM_size = max(self.m.max_POOL_MEM_size, pool_numb)
         is_b = np.zeros(n, bool)
-        a_of = {}
-        for a, b, plan, cost in pairs:
-            is_b[b] = True
-            a_of[int(a)] = (int(b), int(plan), int(cost))
+        pa = np.asarray(pairs).reshape(-1, 4)
+        is_b[pa[:, 1]] = True
+        a_of = dict(zip(pa[:, 0].tolist(), zip(pa[:, 1].tolist(), pa[:, 2].tolist(), pa[:, 3].tolist())))   # last pair of an `a` wins
         out = []
-        for d in range(n):                                                          # analyzePool :760-784
-            if is_b[d]:
-                continue
-            cust = TempDemand(temp_demand[d].id, temp_demand[d].frm, temp_demand[d].to)
-            if d in a_of:
-                b, plan, cost = a_of[d]
-                cust.pool_clnt_id, cust.pool_plan, cust.pool_cost = temp_demand[b].id, plan, cost
-            out.append(cust)
+        for d in np.nonzero(~is_b)[0].tolist():                                     # analyzePool :760-784
+            src = temp_demand[d]
+            hit = a_of.get(d)
+            if hit is None:
+                out.append(TempDemand(src.id, src.frm, src.to))
+            else:
+                out.append(TempDemand(src.id, src.frm, src.to, temp_demand[hit[0]].id, hit[1], hit[2]))
         return out
 
     # ---- helpers :424-494 ----------------------------------------------------------------------------
