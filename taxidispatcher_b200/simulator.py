@@ -110,7 +110,7 @@ class CudaBackend:
         return x
 
 
-@dataclass
+@dataclass(slots=True)
 class TempDemand:      # Simulator.java:47-58
     id: int
     frm: int
@@ -296,7 +296,7 @@ class Simulator:
                         self.assign_pooled_customer(td.pool_clnt_id, cab_id)
                         self.m.total_pickup_numb += 1
             else:
-                demand2.append(TempDemand(td.id, td.frm, td.to, td.pool_clnt_id, td.pool_plan, td.pool_cost))
+                demand2.append(td)                      # records are not modified after find_and_analyze_pool
         return supply2, demand2
 
     # ---- Simulator.java:375-421 ----------------------------------------------------------------------
