@@ -14,7 +14,10 @@
 // exactly `ride > thr` for integer ride.
 //
 // Kernels
-//   pool_prep_cust     per customer {F, T, thr, W}
+//   pool_prepare       one launch for the three independent input passes: per customer {F, T, thr, W} (pool_prep_cust),
+//                      the stand-table check + its copy in the fixed point of the evaluation (pool_check_table), and the
+//                      shortest-path closure D* of the table for the K = 4 pruning bounds (pool_closure: Floyd-Warshall,
+//                      one CTA, cells in registers)
 //   pool_build_lists   per stand s: customers ordered by slack(s,c) = W[c] - D(s,F[c]) descending
 //                      (counting sort, 64 buckets) + cnt[s][w] = #{c : slack >= w}.  The wait rule
 //                      "cumulative pickup distance w + D(s,F[c]) <= W[c]" turns into "c is in the
@@ -36,7 +39,12 @@
 //                      kill their customers, compact, repeat.  Equal to sort + greedy scan because
 //                      the key order is strict.  rank = (p0,p1,..,perm) lexicographic = the
 //                      enumeration order of pool_n.c, i.e. the tie order of a stable sort by cost.
+//                      Records are processed in ascending cost bands (the cheap plans kill most customers before the
+//                      bulk of the list is looked at), the active list is fragmented over the CTAs, and a warp folds
+//                      the keys of consecutive records that share a customer into ONE atomicMin (per-run minima).
 //   pool_emit          kept plans in key order -> 9-int records of pool_n.c:123-134
+//   pool_merge         findpool.c:83-108: the shard outputs are sorted runs, so the global order is a rank by binary
+//                      searches (bitonic sort for rows in any other order), then the same dominance rounds in shared memory
 //
 // Roofline: the enumeration is INT32-issue + shared-memory-lookup bound; compulsory HBM traffic is
 // ~0.4 B per plan.  SURVEY.md section 8(d) defines the logical bytes used for the HBM-fraction
